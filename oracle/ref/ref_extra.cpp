@@ -1,0 +1,88 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY.
+// Small C entry points added next to the reference's own C ABI (FastNoise_C.cpp) inside each
+// oracle/_ref/libfn2ref_*.so: build identification and a threaded driver that follows the
+// reference's documented threading model (one shared const tree, one slab per thread,
+// Generator.h:166-167) for the CPU baseline timing.
+#include <FastNoise/FastNoise_C.h>
+#include <FastSIMD/DispatchClass.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <thread>
+#include <vector>
+
+extern "C"
+{
+    int fn2refLanes() { return FN2SHIM_LANES; }
+    int fn2refRelaxed() { return FN2SHIM_RELAXED; }
+
+    // Generates nx*ny*nz points (row-major, x fastest) into out, splitting z (or y when nz==1)
+    // into `threads` contiguous slabs, each through the ordinary fnGenUniformGrid3D/2D call with a
+    // float slab offset (the reference API has no integer slab origin). Returns seconds of wall time.
+    // dim = 2 uses fnGenUniformGrid2D (nz ignored).
+    double fn2refTimedGridMT( const void* node, float* out, int dim, int nx, int ny, int nz,
+                              float x0, float y0, float z0, float step, int seed, int threads, float* minmax )
+    {
+        if( dim == 2 ) nz = 1;
+        int slabs = dim == 2 ? ny : nz;
+        threads = std::max( 1, std::min( threads, slabs ) );
+        std::vector<float> mm( (size_t)threads * 2 );
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        for( int t = 0; t < threads; t++ )
+        {
+            int begin = (int)( (int64_t)slabs * t / threads );
+            int end = (int)( (int64_t)slabs * ( t + 1 ) / threads );
+            pool.emplace_back( [=, &mm]()
+            {
+                if( dim == 2 )
+                {
+                    fnGenUniformGrid2D( node, out + (size_t)begin * nx, x0, y0 + begin * step, nx, end - begin, step, step, seed, &mm[t * 2] );
+                }
+                else
+                {
+                    fnGenUniformGrid3D( node, out + (size_t)begin * nx * ny, x0, y0, z0 + begin * step, nx, ny, end - begin, step, step, step, seed, &mm[t * 2] );
+                }
+            } );
+        }
+        for( auto& th : pool ) th.join();
+        auto t1 = std::chrono::steady_clock::now();
+        if( minmax )
+        {
+            minmax[0] = mm[0]; minmax[1] = mm[1];
+            for( int t = 1; t < threads; t++ ) { minmax[0] = std::min( minmax[0], mm[t * 2] ); minmax[1] = std::max( minmax[1], mm[t * 2 + 1] ); }
+        }
+        return std::chrono::duration<double>( t1 - t0 ).count();
+    }
+
+    // Same idea for GenPositionArray4D / 3D / 2D: contiguous index ranges per thread.
+    double fn2refTimedPositionsMT( const void* node, float* out, int dim, int count,
+                                   const float* xs, const float* ys, const float* zs, const float* ws,
+                                   int seed, int threads, float* minmax )
+    {
+        threads = std::max( 1, std::min( threads, count ) );
+        std::vector<float> mm( (size_t)threads * 2 );
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        for( int t = 0; t < threads; t++ )
+        {
+            int begin = (int)( (int64_t)count * t / threads );
+            int end = (int)( (int64_t)count * ( t + 1 ) / threads );
+            pool.emplace_back( [=, &mm]()
+            {
+                int n = end - begin;
+                if( dim == 2 ) fnGenPositionArray2D( node, out + begin, n, xs + begin, ys + begin, 0, 0, seed, &mm[t * 2] );
+                else if( dim == 3 ) fnGenPositionArray3D( node, out + begin, n, xs + begin, ys + begin, zs + begin, 0, 0, 0, seed, &mm[t * 2] );
+                else fnGenPositionArray4D( node, out + begin, n, xs + begin, ys + begin, zs + begin, ws + begin, 0, 0, 0, 0, seed, &mm[t * 2] );
+            } );
+        }
+        for( auto& th : pool ) th.join();
+        auto t1 = std::chrono::steady_clock::now();
+        if( minmax )
+        {
+            minmax[0] = mm[0]; minmax[1] = mm[1];
+            for( int t = 1; t < threads; t++ ) { minmax[0] = std::min( minmax[0], mm[t * 2] ); minmax[1] = std::max( minmax[1], mm[t * 2 + 1] ); }
+        }
+        return std::chrono::duration<double>( t1 - t0 ).count();
+    }
+}
