@@ -1,0 +1,497 @@
+// fastnoise2_b200 -- device node library: CellularValue / CellularDistance / CellularLookup.
+// Restates include/FastNoise/Generators/Cellular.inl:18-807. Each thread walks the 3^N neighbourhood of its
+// point; cell points are the cell corner plus a jitter vector taken from bit-fields of the cell hash and
+// normalised with FS::InvSqrt. Template parameters are the node's uniform settings, which the reference
+// branches on per call and the generated program fixes at compile time:
+//   DF     distance function (FastNoise::DistanceFunction value)
+//   SIZEJ  "size jitter" active (constant != 0 or a generator attached, Cellular.inl:27)
+//   TOP    highest index of the sorted-distance / value array that the node reads
+//   PF     callable returning the Minkowski exponent for a delta vector (evaluated AT the delta, Utils.inl:330)
+// Inputs: `seed` already has the node's seed offset added, positions are already multiplied by the
+// frequency, `jitter` is kJitterND * GridJitter and `sizeJitter` is SizeJitter * (-1 / fieldMax).
+#pragma once
+
+namespace fn2
+{
+    constexpr float kJitter2D = 0.437016f;
+    constexpr float kJitter3D = 0.396144f;
+    constexpr float kJitter4D = 0.366025f;
+    constexpr float kSizeJitterScale2D = -1.f / 0x3ff;
+    constexpr float kSizeJitterScale3D = -1.f / 0xffff;
+    constexpr float kSizeJitterScale4D = -1.f / 0xfffff;
+    constexpr float kFltMax = 3.402823466e+38f;
+
+    FN2_DI i32 lsr( i32 v, int s ) { return (i32)( (u32)v >> s ); } // FS::BitShiftRightZeroExtend
+
+    // Jitter direction of a cell from its hash and the factor that scales it to length `jitter`.
+    // [Cellular.inl:57-60] 2D: two 11-bit fields
+    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd )
+    {
+        xd = cvt_f( hash & 0x7ff ) - ( 0x7ff / 2.0f );
+        yd = cvt_f( lsr( hash, 21 ) ) - ( 0x7ff / 2.0f );
+        return jitter * inv_sqrt( fma_( xd, xd, yd * yd ) );
+    }
+    // [Cellular.inl:148-152] 3D: three 10-bit fields at bits 0, 11, 22
+    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd )
+    {
+        xd = cvt_f( hash & 0x3ff ) - ( 0x3ff / 2.0f );
+        yd = cvt_f( ( hash >> 11 ) & 0x3ff ) - ( 0x3ff / 2.0f );
+        zd = cvt_f( lsr( hash, 22 ) ) - ( 0x3ff / 2.0f );
+        return jitter * inv_sqrt( fma_( xd, xd, fma_( yd, yd, zd * zd ) ) );
+    }
+    // [Cellular.inl:247-252] 4D: four bytes
+    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd, float& wd )
+    {
+        xd = cvt_f( hash & 0xff ) - ( 0xff / 2.0f );
+        yd = cvt_f( ( hash >> 8 ) & 0xff ) - ( 0xff / 2.0f );
+        zd = cvt_f( ( hash >> 16 ) & 0xff ) - ( 0xff / 2.0f );
+        wd = cvt_f( lsr( hash, 24 ) ) - ( 0xff / 2.0f );
+        return jitter * inv_sqrt( fma_( xd, xd, fma_( yd, yd, fma_( zd, zd, wd * wd ) ) ) );
+    }
+
+    // per-cell distance multiplier of the size jitter [Cellular.inl:66-70, 160-164, 260-264]
+    FN2_DI float size_jitter2( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( ( hash >> 11 ) & 0x3ff ), 1.0f ); }
+    FN2_DI float size_jitter3( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xffff ), 1.0f ); }
+    FN2_DI float size_jitter4( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xfffff ), 1.0f ); }
+
+    // insert into the ascending (distance, hash) list, entries 0..TOP [Cellular.inl:72-89]
+    template<int TOP>
+    FN2_DI void value_insert( float ( &distance )[4], i32 ( &valueHash )[4], float newDistance, i32 newHash )
+    {
+#pragma unroll
+        for( int i = 0; i <= TOP; i++ )
+        {
+            bool closer = newDistance < distance[i];
+            float localDistance = distance[i];
+            i32 localHash = valueHash[i];
+            distance[i] = closer ? newDistance : distance[i];
+            valueHash[i] = closer ? newHash : valueHash[i];
+            newDistance = closer ? localDistance : newDistance;
+            newHash = closer ? localHash : newHash;
+        }
+    }
+
+    // sorting network step of CellularDistance, entries 0..TOP [Cellular.inl:344-349]
+    template<int TOP>
+    FN2_DI void distance_insert( float ( &distance )[4], float newDistance )
+    {
+#pragma unroll
+        for( int i = TOP; i > 0; i-- )
+        {
+            distance[i] = max_( min_( distance[i], newDistance ), distance[i - 1] );
+        }
+        distance[0] = min_( distance[0], newDistance );
+    }
+
+    // ================================================================== CellularValue [Cellular.inl:18-292]
+    // returns the hash of the TOP-th closest cell (caller converts and range-maps it)
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI i32 cellular_value2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP )
+    {
+        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        i32 valueHash[4] = { 0, 0, 0, 0 };
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y;
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                i32 hash = hash_hb( seed, xc, yc );
+                float xd, yd;
+                float invMag = cell_vector( hash, jitter, xd, yd );
+                xd = fma_( xd, invMag, xcf );
+                yd = fma_( yd, invMag, ycf );
+                float newDistance = calc_distance<DF, true>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
+                value_insert<TOP>( distance, valueHash, newDistance, hash );
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+        return valueHash[TOP];
+    }
+
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI i32 cellular_value3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP )
+    {
+        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        i32 valueHash[4] = { 0, 0, 0, 0 };
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z;
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    i32 hash = hash_hb( seed, xc, yc, zc );
+                    float xd, yd, zd;
+                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    xd = fma_( xd, invMag, xcf );
+                    yd = fma_( yd, invMag, ycf );
+                    zd = fma_( zd, invMag, zcf );
+                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
+                    value_insert<TOP>( distance, valueHash, newDistance, hash );
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+        return valueHash[TOP];
+    }
+
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI i32 cellular_value4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP )
+    {
+        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        i32 valueHash[4] = { 0, 0, 0, 0 };
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z, wcfBase = cvt_f( wcBase ) - w;
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+        wcBase = imul( wcBase, kPW );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    float wcf = wcfBase;
+                    i32 wc = wcBase;
+                    for( int wi = 0; wi < 3; wi++ )
+                    {
+                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
+                        float xd, yd, zd, wd;
+                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        xd = fma_( xd, invMag, xcf );
+                        yd = fma_( yd, invMag, ycf );
+                        zd = fma_( zd, invMag, zcf );
+                        wd = fma_( wd, invMag, wcf );
+                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
+                        value_insert<TOP>( distance, valueHash, newDistance, hash );
+                        wcf += 1.0f;
+                        wc = iadd( wc, kPW );
+                    }
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+        return valueHash[TOP];
+    }
+
+    // ================================================================== CellularDistance [Cellular.inl:295-529]
+    // fills distance[0..TOP] with the ascending cell distances
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI void cellular_distance2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    {
+        distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float xcfOffset = xcf - x;
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                i32 hash = hash_hb( seed, xc, yc );
+                float xd, yd;
+                float invMag = cell_vector( hash, jitter, xd, yd );
+                xd = fma_( xd, invMag, xcfOffset );
+                yd = fma_( yd, invMag, ycf - y );
+                float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
+                distance_insert<TOP>( distance, newDistance );
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI void cellular_distance3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    {
+        distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float xcfOffset = xcf - x;
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float ycfOffset = ycf - y;
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    i32 hash = hash_hb( seed, xc, yc, zc );
+                    float xd, yd, zd;
+                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    xd = fma_( xd, invMag, xcfOffset );
+                    yd = fma_( yd, invMag, ycfOffset );
+                    zd = fma_( zd, invMag, zcf - z );
+                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
+                    distance_insert<TOP>( distance, newDistance );
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+
+    template<int DF, bool SIZEJ, int TOP, class PF>
+    FN2_DI void cellular_distance4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    {
+        distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+        wcBase = imul( wcBase, kPW );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float xcfOffset = xcf - x;
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float ycfOffset = ycf - y;
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    float zcfOffset = zcf - z;
+                    float wcf = wcfBase;
+                    i32 wc = wcBase;
+                    for( int wi = 0; wi < 3; wi++ )
+                    {
+                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
+                        float xd, yd, zd, wd;
+                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        xd = fma_( xd, invMag, xcfOffset );
+                        yd = fma_( yd, invMag, ycfOffset );
+                        zd = fma_( zd, invMag, zcfOffset );
+                        wd = fma_( wd, invMag, wcf - w );
+                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
+                        distance_insert<TOP>( distance, newDistance );
+                        wcf += 1.0f;
+                        wc = iadd( wc, kPW );
+                    }
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+
+    // ================================================================== CellularLookup [Cellular.inl:569-806]
+    // writes the jittered centre of the closest cell
+    template<int DF, bool SIZEJ, class PF>
+    FN2_DI void cellular_lookup2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP, float& cellX, float& cellY )
+    {
+        float distance = kFltMax;
+        cellX = cellY = 0.0f;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                i32 hash = hash_hb( seed, xc, yc );
+                float xd, yd;
+                float invMag = cell_vector( hash, jitter, xd, yd );
+                float localX = fma_( xd, invMag, xcf );
+                float localY = fma_( yd, invMag, ycf );
+                xd = localX - x;
+                yd = localY - y;
+                float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
+                bool closer = newDistance < distance;
+                distance = min_( newDistance, distance );
+                cellX = closer ? localX : cellX;
+                cellY = closer ? localY : cellY;
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+
+    template<int DF, bool SIZEJ, class PF>
+    FN2_DI void cellular_lookup3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP, float& cellX, float& cellY, float& cellZ )
+    {
+        float distance = kFltMax;
+        cellX = cellY = cellZ = 0.0f;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    i32 hash = hash_hb( seed, xc, yc, zc );
+                    float xd, yd, zd;
+                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    float localX = fma_( xd, invMag, xcf );
+                    float localY = fma_( yd, invMag, ycf );
+                    float localZ = fma_( zd, invMag, zcf );
+                    xd = localX - x;
+                    yd = localY - y;
+                    zd = localZ - z;
+                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
+                    bool closer = newDistance < distance;
+                    distance = min_( newDistance, distance );
+                    cellX = closer ? localX : cellX;
+                    cellY = closer ? localY : cellY;
+                    cellZ = closer ? localZ : cellZ;
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+
+    template<int DF, bool SIZEJ, class PF>
+    FN2_DI void cellular_lookup4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP,
+                                  float& cellX, float& cellY, float& cellZ, float& cellW )
+    {
+        float distance = kFltMax;
+        cellX = cellY = cellZ = cellW = 0.0f;
+
+        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
+        xc = imul( xc, kPX );
+        ycBase = imul( ycBase, kPY );
+        zcBase = imul( zcBase, kPZ );
+        wcBase = imul( wcBase, kPW );
+
+        for( int xi = 0; xi < 3; xi++ )
+        {
+            float ycf = ycfBase;
+            i32 yc = ycBase;
+            for( int yi = 0; yi < 3; yi++ )
+            {
+                float zcf = zcfBase;
+                i32 zc = zcBase;
+                for( int zi = 0; zi < 3; zi++ )
+                {
+                    float wcf = wcfBase;
+                    i32 wc = wcBase;
+                    for( int wi = 0; wi < 3; wi++ )
+                    {
+                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
+                        float xd, yd, zd, wd;
+                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        float localX = fma_( xd, invMag, xcf );
+                        float localY = fma_( yd, invMag, ycf );
+                        float localZ = fma_( zd, invMag, zcf );
+                        float localW = fma_( wd, invMag, wcf );
+                        xd = localX - x;
+                        yd = localY - y;
+                        zd = localZ - z;
+                        wd = localW - w;
+                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
+                        bool closer = newDistance < distance;
+                        distance = min_( newDistance, distance );
+                        cellX = closer ? localX : cellX;
+                        cellY = closer ? localY : cellY;
+                        cellZ = closer ? localZ : cellZ;
+                        cellW = closer ? localW : cellW;
+                        wcf += 1.0f;
+                        wc = iadd( wc, kPW );
+                    }
+                    zcf += 1.0f;
+                    zc = iadd( zc, kPZ );
+                }
+                ycf += 1.0f;
+                yc = iadd( yc, kPY );
+            }
+            xcf += 1.0f;
+            xc = iadd( xc, kPX );
+        }
+    }
+}

@@ -1,0 +1,305 @@
+// fastnoise2_b200 -- device node library: SuperSimplex 2D/3D/4D (un-normalised values).
+// Restates include/FastNoise/Generators/Simplex.inl:293-936 as scalar per-thread code; the vertex
+// contributions are accumulated in the reference's order so the fma chain rounds identically.
+#pragma once
+
+namespace fn2
+{
+    constexpr float kSuperSimplexBound2 = 0.14084912836551666259765625f;
+    constexpr float kSuperSimplexBound3 = 0.0069091119803488254547119140625f;
+    constexpr float kSuperSimplexBound4 = (float)0.011310013942420482635498046875;
+
+    FN2_DI float sq2( float v ) { return ( v * v ) * ( v * v ); }
+    FN2_DI i32 signbit_if( bool c ) { return c ? (i32)0x80000000u : 0; }
+    // base +- prime, by sign mask [Simplex.inl:475 and siblings]
+    FN2_DI i32 step_prime( i32 base, i32 prime, bool negative ) { return iadd( base, negative ? isub( 0, prime ) : prime ); }
+
+    // [Simplex.inl:293-377]
+    FN2_DI float supersimplex2( i32 seed, float x, float y )
+    {
+        constexpr double kSkew2 = 1.0 / ( kRoot3 + 1.0 );
+        constexpr double kUnskew2 = -1.0 / ( kRoot3 + 3.0 );
+        constexpr float kR2 = (float)( 2.0 / 3.0 );
+
+        float skewDelta = (float)kSkew2 * ( x + y );
+        float xSkewed = x + skewDelta, ySkewed = y + skewDelta;
+        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed );
+        float dxS = xSkewed - xBase, dyS = ySkewed - yBase;
+        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY );
+
+        bool forwardXY = dxS + dyS > 1.0f;
+        float boundaryXY = forwardXY ? -1.0f : 0.0f;
+        bool forwardX = fma_( dxS, -2.0f, dyS ) < boundaryXY;
+        bool forwardY = fma_( dyS, -2.0f, dxS ) < boundaryXY;
+
+        float unskewDelta = (float)kUnskew2 * ( dxS + dyS );
+        float dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
+
+        float falloffBase0, value;
+        { // vertex <0,0>
+            float g = grad_dot2( hash_primes( seed, xP, yP ), dxBase, dyBase );
+            falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
+            value = pow4( falloffBase0 ) * g;
+        }
+        { // vertex <1,1>
+            float g = grad_dot2( hash_primes( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ) );
+            float falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
+            value = fma_( pow4( falloff ), g, value );
+        }
+
+        float xyDelta = forwardXY ? (float)( kUnskew2 + 1 ) : (float)( -kUnskew2 );
+        dxBase -= xyDelta;
+        dyBase -= xyDelta;
+
+        { // vertex <1,0> or <-1,0> or <1,2>
+            i32 xv = forwardX ? iadd( xP, imul( kPX, 2 ) ) : xP;
+            xv = forwardXY ? xv : isub( xv, kPX );
+            i32 yv = forwardXY ? iadd( yP, kPY ) : yP;
+            float dx = dxBase - ( forwardX ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
+            float dy = forwardX ? dyBase - (float)( 2 * kUnskew2 ) : dyBase;
+            float g = grad_dot2( hash_primes( seed, xv, yv ), dx, dy );
+            float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
+            value = fma_( pow4( falloff ), g, value );
+        }
+        { // vertex <0,1> or <0,-1> or <2,1>
+            i32 xv = forwardXY ? iadd( xP, kPX ) : xP;
+            i32 yv = forwardY ? iadd( yP, imul( kPY, 2 ) ) : yP;
+            yv = forwardXY ? yv : isub( yv, kPY );
+            float dx = forwardY ? dxBase - (float)( 2 * kUnskew2 ) : dxBase;
+            float dy = dyBase - ( forwardY ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
+            float g = grad_dot2( hash_primes( seed, xv, yv ), dx, dy );
+            float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
+            value = fma_( pow4( falloff ), g, value );
+        }
+        return value;
+    }
+
+    // [Simplex.inl:379-576]
+    FN2_DI float supersimplex3( i32 seed, float x, float y, float z )
+    {
+        constexpr double kSkew3 = 1.0 / 3.0;
+        constexpr double kReflectUnskew3 = -1.0 / 2.0;
+        constexpr double kTwiceUnskew3 = -1.0 / 4.0;
+        constexpr double kDistanceSquaredA = 3.0 / 4.0;
+        constexpr double kDistanceSquaredB = 1.0;
+        constexpr float kR2 = (float)kDistanceSquaredA;
+
+        float skewDelta = (float)kSkew3 * ( x + y + z );
+        float xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta;
+        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed );
+        float dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase;
+
+        { // closest lattice vertex of the unit cell [:405-441]
+            float tud = (float)kTwiceUnskew3 * ( dxS + dyS + dzS );
+            float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
+            float xyzN = -tud;
+
+            float maxScore = 0.375f;
+            i32 bits = xyzN > maxScore ? -1 : 0;
+            maxScore = max_( maxScore, xyzN );
+#define FN2_CONSIDER( SCORE, BITS ) { float sc = SCORE; bits = sc > maxScore ? BITS : bits; maxScore = max_( maxScore, sc ); }
+            FN2_CONSIDER( xN, 1 )
+            FN2_CONSIDER( yN, 2 )
+            FN2_CONSIDER( zN, 4 )
+            maxScore += 0.125f - xyzN;
+            FN2_CONSIDER( -zN, 3 )
+            FN2_CONSIDER( -yN, 5 )
+            FN2_CONSIDER( -xN, 6 )
+
+            bool moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0;
+            xBase = moveX ? xBase + 1.0f : xBase;
+            yBase = moveY ? yBase + 1.0f : yBase;
+            zBase = moveZ ? zBase + 1.0f : zBase;
+            dxS = moveX ? dxS - 1.0f : dxS;
+            dyS = moveY ? dyS - 1.0f : dyS;
+            dzS = moveZ ? dzS - 1.0f : dzS;
+        }
+
+        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ );
+
+        float sum = dxS + dyS + dzS;
+        float tud = (float)kTwiceUnskew3 * sum;
+        float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
+        float xyzN = -tud;
+
+        float ud = (float)kReflectUnskew3 * sum;
+        float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud;
+        float coordSum = (float)( 1 + 3 * kReflectUnskew3 ) * sum;
+
+        float value, stemA, stemB;
+        { // <0,0,0>
+            float g = grad_dot3( hash_primes( seed, xP, yP, zP ), dxB, dyB, dzB );
+            float fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
+            stemA = fb - (float)( kDistanceSquaredA * 0.5 );
+            stemB = fb - (float)( kDistanceSquaredB * 0.5 );
+            value = sq2( fb ) * g;
+        }
+        { // <1,1,1> or <-1,-1,-1>
+            bool sm = xyzN < 0.0f;
+            i32 sign = signbit_if( sm );
+            float o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
+            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o );
+            float fb = max_( fma_( o, coordSum, stemA ), 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <1,1,0> or <-1,-1,0>
+            bool sm = xyzN < zN;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0 );
+            float fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <1,0,1> or <-1,0,-1>
+            bool sm = xyzN < yN;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB );
+            float fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <0,1,1> or <0,-1,-1>
+            bool sm = xyzN < xN;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            float g = grad_dot3( hash_primes( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB );
+            float fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <1,0,0> or <-1,0,0>
+            bool sm = xN < 0.0f;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)kReflectUnskew3, sign );
+            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0 );
+            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <0,1,0> or <0,-1,0>
+            bool sm = yN < 0.0f;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)kReflectUnskew3, sign );
+            float g = grad_dot3( hash_primes( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0 );
+            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        { // <0,0,1> or <0,0,-1>
+            bool sm = zN < 0.0f;
+            i32 sign = signbit_if( sm );
+            float o0 = fxor( (float)kReflectUnskew3, sign );
+            float g = grad_dot3( hash_primes( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0 );
+            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
+            value = fma_( sq2( fb ), g, value );
+        }
+        return value;
+    }
+
+    // [Simplex.inl:578-936]
+    FN2_DI float supersimplex4( i32 seed, float x, float y, float z, float w )
+    {
+        constexpr double kSkew4 = 1.0 / ( kRoot5 + 1.0 );
+        constexpr double kUnskew4 = -1.0 / ( kRoot5 + 5.0 );
+        constexpr double kTwiceUnskew4 = -1.0 / 5.0;
+        constexpr double kDistanceSquaredA = 4.0 / 5.0;
+        constexpr double kDistanceSquaredB = 6.0 / 5.0;
+        constexpr float kR2 = (float)kDistanceSquaredA;
+
+        float skewDelta = (float)kSkew4 * ( x + y + z + w );
+        float xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta, wSkewed = w + skewDelta;
+        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed ), wBase = floor_( wSkewed );
+        float dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase, dwS = wSkewed - wBase;
+
+        { // closest lattice vertex of the unit cell [:608-659]
+            float tud = (float)kTwiceUnskew4 * ( dxS + dyS + dzS + dwS );
+            float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
+            float xyzwN = -tud;
+
+            float maxScore = 0.6f - xyzwN;
+            i32 bits = 0.2f > maxScore ? -1 : 0;
+            maxScore = max_( maxScore, 0.2f );
+            FN2_CONSIDER( -wN, 7 )
+            FN2_CONSIDER( -zN, 11 )
+            FN2_CONSIDER( -yN, 13 )
+            FN2_CONSIDER( -xN, 14 )
+            maxScore += xyzwN - 0.2f;
+            FN2_CONSIDER( xN, 1 )
+            FN2_CONSIDER( yN, 2 )
+            FN2_CONSIDER( zN, 4 )
+            FN2_CONSIDER( wN, 8 )
+            maxScore += 0.2f - xN;
+            FN2_CONSIDER( yN, 3 )
+            FN2_CONSIDER( zN, 5 )
+            FN2_CONSIDER( wN, 9 )
+            maxScore += xN;
+            FN2_CONSIDER( yN + zN, 6 )
+            maxScore -= wN;
+            FN2_CONSIDER( yN, 10 )
+            FN2_CONSIDER( zN, 12 )
+#undef FN2_CONSIDER
+
+            bool moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0, moveW = ( bits & 8 ) != 0;
+            xBase = moveX ? xBase + 1.0f : xBase;
+            yBase = moveY ? yBase + 1.0f : yBase;
+            zBase = moveZ ? zBase + 1.0f : zBase;
+            wBase = moveW ? wBase + 1.0f : wBase;
+            dxS = moveX ? dxS - 1.0f : dxS;
+            dyS = moveY ? dyS - 1.0f : dyS;
+            dzS = moveZ ? dzS - 1.0f : dzS;
+            dwS = moveW ? dwS - 1.0f : dwS;
+        }
+
+        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ ), wP = imul( cvt_i( wBase ), kPW );
+
+        float sum = dxS + dyS + dzS + dwS;
+        float tud = (float)kTwiceUnskew4 * sum;
+        float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
+        float xyzwN = -tud;
+
+        float ud = (float)kUnskew4 * sum;
+        float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud, dwB = dwS + ud;
+        float coordSum = (float)( 1 + 4 * kUnskew4 ) * sum;
+
+        float value, stemA, stemB;
+        { // <0,0,0,0>
+            float g = grad_dot4( hash_primes( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB );
+            float fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
+            stemA = fb - (float)( kDistanceSquaredA * 0.5 );
+            stemB = fb - (float)( kDistanceSquaredB * 0.5 );
+            value = sq2( fb ) * g;
+        }
+
+        // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many.
+        // Coordinates on stepping axes use offset1 = (K*u + 1)^sign, the others offset0 = (K*u)^sign. FALLOFF is
+        // the vertex-class specific falloff base expression [Simplex.inl:692-931].
+#define FN2_SS4_VERTEX( COND, MX, MY, MZ, MW, K, FALLOFF ) \
+        { \
+            bool sm = COND; \
+            i32 sign = signbit_if( sm ); \
+            float o1 = fxor( (float)( K * kUnskew4 + 1 ), sign ); \
+            float o0 = fxor( (float)( K * kUnskew4 ), sign ); \
+            (void)o0; \
+            float g = grad_dot4( hash_primes( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
+                                              MZ ? step_prime( zP, kPZ, sm ) : zP, MW ? step_prime( wP, kPW, sm ) : wP ), \
+                                 dxB - ( MX ? o1 : o0 ), dyB - ( MY ? o1 : o0 ), dzB - ( MZ ? o1 : o0 ), dwB - ( MW ? o1 : o0 ) ); \
+            float fb = max_( FALLOFF, 0.0f ); \
+            value = fma_( sq2( fb ), g, value ); \
+        }
+
+        FN2_SS4_VERTEX( xyzwN < 0.0f, 1, 1, 1, 1, 4, fma_( o1, coordSum, stemA ) )
+        FN2_SS4_VERTEX( xyzwN < wN, 1, 1, 1, 0, 3, fma_( o1, coordSum, stemB ) - fxor( dwB, sign ) )
+        FN2_SS4_VERTEX( xyzwN < zN, 1, 1, 0, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dzB, sign ) )
+        FN2_SS4_VERTEX( xyzwN < yN, 1, 0, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dyB, sign ) )
+        FN2_SS4_VERTEX( xyzwN < xN, 0, 1, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dxB, sign ) )
+        FN2_SS4_VERTEX( xN < 0.0f, 1, 0, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dxB, sign ) )
+        FN2_SS4_VERTEX( xN < -yN, 1, 1, 0, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dyB, sign ) )
+        FN2_SS4_VERTEX( xN < -zN, 1, 0, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dzB, sign ) )
+        FN2_SS4_VERTEX( xN < -wN, 1, 0, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dwB, sign ) )
+        FN2_SS4_VERTEX( yN < 0.0f, 0, 1, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dyB, sign ) )
+        FN2_SS4_VERTEX( yN < -zN, 0, 1, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dzB, sign ) )
+        FN2_SS4_VERTEX( yN < -wN, 0, 1, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dwB, sign ) )
+        FN2_SS4_VERTEX( zN < 0.0f, 0, 0, 1, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dzB, sign ) )
+        FN2_SS4_VERTEX( zN < -wN, 0, 0, 1, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dzB + dwB, sign ) )
+        FN2_SS4_VERTEX( wN < 0.0f, 0, 0, 0, 1, 1, fma_( o0, coordSum, stemA ) + fxor( dwB, sign ) )
+#undef FN2_SS4_VERTEX
+        return value;
+    }
+}

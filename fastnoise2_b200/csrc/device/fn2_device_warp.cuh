@@ -1,0 +1,127 @@
+// fastnoise2_b200 -- device node library: DomainWarpGradient displacement field.
+// Restates include/FastNoise/Generators/DomainWarp.inl:33-206: a value-noise-like vector field whose
+// components are bit-fields of the corner hashes, blended with Hermite weights. `seed` already includes the
+// node's seed offset, (x,y,..) is the position times the warp frequency, (xOut,yOut,..) is the position being
+// displaced and (ax,ay,..) the per-axis amplitude scaling. Returns the squared length of the unit-range warp
+// vector (the "strength" the fractal warps feed back into the amplitude).
+#pragma once
+
+namespace fn2
+{
+    FN2_DI float warp_gradient2( i32 seed, float warpAmp, float x, float y, float& xOut, float& yOut, float ax, float ay )
+    {
+        float xs = floor_( x ), ys = floor_( y );
+        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY );
+        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY );
+        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys );
+        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1;
+        const float normalise = 1.0f / ( 0xffff / 2.0f );
+
+        float xWarp, yWarp;
+        {
+            i32 h = hash_hb( seed, x0, y0 );
+            float c = xs0 * ys0;
+            xWarp = c * cvt_f( h & 0xffff );
+            yWarp = c * cvt_f( lsr( h, 16 ) );
+        }
+#define FN2_CORNER( XS, YS, XP, YP ) { i32 h = hash_hb( seed, XP, YP ); float c = XS * YS; \
+            xWarp = fma_( c, cvt_f( h & 0xffff ), xWarp ); yWarp = fma_( c, cvt_f( lsr( h, 16 ) ), yWarp ); }
+        FN2_CORNER( xs1, ys0, x1, y0 )
+        FN2_CORNER( xs0, ys1, x0, y1 )
+        FN2_CORNER( xs1, ys1, x1, y1 )
+#undef FN2_CORNER
+
+        xWarp = fms_( xWarp, normalise, 1.0f );
+        yWarp = fms_( yWarp, normalise, 1.0f );
+        xOut = fma_( xWarp, warpAmp * ax, xOut );
+        yOut = fma_( yWarp, warpAmp * ay, yOut );
+        return fma_( xWarp, xWarp, yWarp * yWarp );
+    }
+
+    FN2_DI float warp_gradient3( i32 seed, float warpAmp, float x, float y, float z, float& xOut, float& yOut, float& zOut, float ax, float ay, float az )
+    {
+        float xs = floor_( x ), ys = floor_( y ), zs = floor_( z );
+        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ );
+        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ );
+        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs );
+        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1;
+        const float normalise = 1.0f / ( 0x3ff / 2.0f );
+
+        float xWarp, yWarp, zWarp;
+        {
+            i32 h = hash_hb( seed, x0, y0, z0 );
+            float c = xs0 * ys0 * zs0;
+            xWarp = c * cvt_f( h & 0x3ff );
+            yWarp = c * cvt_f( ( h >> 11 ) & 0x3ff );
+            zWarp = c * cvt_f( lsr( h, 22 ) );
+        }
+#define FN2_CORNER( XS, YS, ZS, XP, YP, ZP ) { i32 h = hash_hb( seed, XP, YP, ZP ); float c = XS * YS * ZS; \
+            xWarp = fma_( c, cvt_f( h & 0x3ff ), xWarp ); yWarp = fma_( c, cvt_f( ( h >> 11 ) & 0x3ff ), yWarp ); zWarp = fma_( c, cvt_f( lsr( h, 22 ) ), zWarp ); }
+        FN2_CORNER( xs1, ys0, zs0, x1, y0, z0 )
+        FN2_CORNER( xs0, ys1, zs0, x0, y1, z0 )
+        FN2_CORNER( xs1, ys1, zs0, x1, y1, z0 )
+        FN2_CORNER( xs0, ys0, zs1, x0, y0, z1 )
+        FN2_CORNER( xs1, ys0, zs1, x1, y0, z1 )
+        FN2_CORNER( xs0, ys1, zs1, x0, y1, z1 )
+        FN2_CORNER( xs1, ys1, zs1, x1, y1, z1 )
+#undef FN2_CORNER
+
+        xWarp = fms_( xWarp, normalise, 1.0f );
+        yWarp = fms_( yWarp, normalise, 1.0f );
+        zWarp = fms_( zWarp, normalise, 1.0f );
+        xOut = fma_( xWarp, warpAmp * ax, xOut );
+        yOut = fma_( yWarp, warpAmp * ay, yOut );
+        zOut = fma_( zWarp, warpAmp * az, zOut );
+        return fma_( xWarp, xWarp, fma_( yWarp, yWarp, zWarp * zWarp ) );
+    }
+
+    FN2_DI float warp_gradient4( i32 seed, float warpAmp, float x, float y, float z, float w,
+                                 float& xOut, float& yOut, float& zOut, float& wOut, float ax, float ay, float az, float aw )
+    {
+        float xs = floor_( x ), ys = floor_( y ), zs = floor_( z ), ws = floor_( w );
+        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ ), w0 = imul( cvt_i( ws ), kPW );
+        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ ), w1 = iadd( w0, kPW );
+        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs ), ws1 = hermite( w - ws );
+        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1, ws0 = 1.0f - ws1;
+        const float normalise = 1.0f / ( 0xff / 2.0f );
+
+        float xWarp, yWarp, zWarp, wWarp;
+        {
+            i32 h = hash_hb( seed, x0, y0, z0, w0 );
+            float c = xs0 * ys0 * zs0 * ws0;
+            xWarp = c * cvt_f( h & 0xff );
+            yWarp = c * cvt_f( ( h >> 8 ) & 0xff );
+            zWarp = c * cvt_f( ( h >> 16 ) & 0xff );
+            wWarp = c * cvt_f( lsr( h, 24 ) );
+        }
+#define FN2_CORNER( XS, YS, ZS, WS, XP, YP, ZP, WP ) { i32 h = hash_hb( seed, XP, YP, ZP, WP ); float c = XS * YS * ZS * WS; \
+            xWarp = fma_( c, cvt_f( h & 0xff ), xWarp ); yWarp = fma_( c, cvt_f( ( h >> 8 ) & 0xff ), yWarp ); \
+            zWarp = fma_( c, cvt_f( ( h >> 16 ) & 0xff ), zWarp ); wWarp = fma_( c, cvt_f( lsr( h, 24 ) ), wWarp ); }
+        FN2_CORNER( xs1, ys0, zs0, ws0, x1, y0, z0, w0 )
+        FN2_CORNER( xs0, ys1, zs0, ws0, x0, y1, z0, w0 )
+        FN2_CORNER( xs1, ys1, zs0, ws0, x1, y1, z0, w0 )
+        FN2_CORNER( xs0, ys0, zs1, ws0, x0, y0, z1, w0 )
+        FN2_CORNER( xs1, ys0, zs1, ws0, x1, y0, z1, w0 )
+        FN2_CORNER( xs0, ys1, zs1, ws0, x0, y1, z1, w0 )
+        FN2_CORNER( xs1, ys1, zs1, ws0, x1, y1, z1, w0 )
+        FN2_CORNER( xs0, ys0, zs0, ws1, x0, y0, z0, w1 )
+        FN2_CORNER( xs1, ys0, zs0, ws1, x1, y0, z0, w1 )
+        FN2_CORNER( xs0, ys1, zs0, ws1, x0, y1, z0, w1 )
+        FN2_CORNER( xs1, ys1, zs0, ws1, x1, y1, z0, w1 )
+        FN2_CORNER( xs0, ys0, zs1, ws1, x0, y0, z1, w1 )
+        FN2_CORNER( xs1, ys0, zs1, ws1, x1, y0, z1, w1 )
+        FN2_CORNER( xs0, ys1, zs1, ws1, x0, y1, z1, w1 )
+        FN2_CORNER( xs1, ys1, zs1, ws1, x1, y1, z1, w1 )
+#undef FN2_CORNER
+
+        xWarp = fms_( xWarp, normalise, 1.0f );
+        yWarp = fms_( yWarp, normalise, 1.0f );
+        zWarp = fms_( zWarp, normalise, 1.0f );
+        wWarp = fms_( wWarp, normalise, 1.0f );
+        xOut = fma_( xWarp, warpAmp * ax, xOut );
+        yOut = fma_( yWarp, warpAmp * ay, yOut );
+        zOut = fma_( zWarp, warpAmp * az, zOut );
+        wOut = fma_( wWarp, warpAmp * aw, wOut );
+        return fma_( xWarp, xWarp, fma_( yWarp, yWarp, fma_( zWarp, zWarp, wWarp * wWarp ) ) );
+    }
+}

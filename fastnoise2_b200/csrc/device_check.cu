@@ -1,0 +1,56 @@
+// fastnoise2_b200 -- ahead-of-time compile check of the device node library.
+// The product path compiles device/fn2_device*.cuh through NVRTC once per tree; this translation unit makes
+// nvcc compile the same text for sm_100a at build time (syntax, -Xptxas -v register counts, cuobjdump -sass)
+// and provides one fixed kernel per leaf so the library can be smoke-tested without NVRTC.
+#define FN2_RELAXED 0
+#include "fn2_device.cuh"
+
+namespace
+{
+    struct ConstP
+    {
+        float p;
+        __device__ float operator()( float, float ) const { return p; }
+        __device__ float operator()( float, float, float ) const { return p; }
+        __device__ float operator()( float, float, float, float ) const { return p; }
+    };
+}
+
+// which = leaf selector; evaluates one point per thread at ( i*step, i*step*0.7, i*step*0.3, i*step*0.1 )
+extern "C" __global__ void __launch_bounds__( 256 ) fn2_device_check( float* __restrict__ out, int n, int which, int seed, float step )
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if( i >= n ) return;
+    const float x = i * step, y = x * 0.7f, z = x * 0.3f, w = x * 0.1f;
+    float v = 0;
+    float d[4];
+    float cx, cy, cz, cw;
+    switch( which )
+    {
+    case 0: v = fn2::simplex2( seed, x, y ); break;
+    case 1: v = fn2::simplex3( seed, x, y, z ); break;
+    case 2: v = fn2::simplex4( seed, x, y, z, w ); break;
+    case 3: v = fn2::supersimplex2( seed, x, y ); break;
+    case 4: v = fn2::supersimplex3( seed, x, y, z ); break;
+    case 5: v = fn2::supersimplex4( seed, x, y, z, w ); break;
+    case 6: v = fn2::perlin2( seed, x, y ); break;
+    case 7: v = fn2::perlin3( seed, x, y, z ); break;
+    case 8: v = fn2::perlin4( seed, x, y, z, w ); break;
+    case 9: v = fn2::value2( seed, x, y ) + fn2::value3( seed, x, y, z ) + fn2::value4( seed, x, y, z, w ); break;
+    case 10: v = fn2::white( seed, x, y ) + fn2::white( seed, x, y, z ) + fn2::white( seed, x, y, z, w ); break;
+    case 11: fn2::cellular_distance2<1, false, 1>( seed, x, y, 0.4f, 0.0f, ConstP { 1.5f }, d ); v = d[0] + d[1]; break;
+    case 12: fn2::cellular_distance3<1, false, 0>( seed, x, y, z, 0.4f, 0.0f, ConstP { 1.5f }, d ); v = d[0]; break;
+    case 13: fn2::cellular_distance4<5, true, 3>( seed, x, y, z, w, 0.4f, 0.001f, ConstP { 1.5f }, d ); v = d[3]; break;
+    case 14: v = fn2::cvt_f( fn2::cellular_value2<0, false, 0>( seed, x, y, 0.4f, 0.0f, ConstP { 1.5f } ) ); break;
+    case 15: v = fn2::cvt_f( fn2::cellular_value3<2, true, 2>( seed, x, y, z, 0.4f, 0.001f, ConstP { 1.5f } ) ); break;
+    case 16: v = fn2::cvt_f( fn2::cellular_value4<3, false, 1>( seed, x, y, z, w, 0.4f, 0.0f, ConstP { 1.5f } ) ); break;
+    case 17: fn2::cellular_lookup2<1, false>( seed, x, y, 0.4f, 0.0f, ConstP { 1.5f }, cx, cy ); v = cx + cy; break;
+    case 18: fn2::cellular_lookup3<1, false>( seed, x, y, z, 0.4f, 0.0f, ConstP { 1.5f }, cx, cy, cz ); v = cx + cy + cz; break;
+    case 19: fn2::cellular_lookup4<4, true>( seed, x, y, z, w, 0.4f, 0.001f, ConstP { 1.5f }, cx, cy, cz, cw ); v = cx + cy + cz + cw; break;
+    case 20: { float a = x, b = y; v = fn2::warp_gradient2( seed, 30.f, x * 0.01f, y * 0.01f, a, b, 1.f, 1.f ) + a + b; break; }
+    case 21: { float a = x, b = y, c = z; v = fn2::warp_gradient3( seed, 30.f, x * 0.01f, y * 0.01f, z * 0.01f, a, b, c, 1.f, 1.f, 1.f ) + a + b + c; break; }
+    case 22: { float a = x, b = y, c = z, e = w; v = fn2::warp_gradient4( seed, 30.f, x * 0.01f, y * 0.01f, z * 0.01f, w * 0.01f, a, b, c, e, 1.f, 1.f, 1.f, 1.f ) + a + b + c + e; break; }
+    case 23: v = fn2::sinewave( x, y, z, w ) + fn2::checkerboard( x, y, z ) + fn2::pow_pos( fn2::abs_( x ) + 0.5f, 1.5f ) + fn2::modulus( x, 3.0f ); break;
+    }
+    out[i] = v;
+}

@@ -1,0 +1,843 @@
+// fastnoise2_b200 -- lowering: node tree -> CUDA source of one fused kernel.
+//
+// The reference evaluates a tree by virtual calls, one per child per SIMD vector
+// (Generators/Generator.inl:48-67 GetSourceValue). Here the tree rooted at the node a Gen* call was made on
+// is turned into straight-line device code: one `n<K>_<D>` function per (node, dimensionality) reached,
+// with every uniform parameter folded in as a literal and every uniform branch of the reference (distance
+// function, return type, interpolation, "is this hybrid a node?") resolved while generating. The functions
+// call the hand-written bodies in device/fn2_device*.cuh. Shared sub-trees are emitted once. The entry
+// kernel appended at the end is the batch driver for one call shape (grid 2/3/4D, tileable, positions).
+#include <FastNoise/FastNoise.h>
+#include <FastNoise/Metadata.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <unordered_map>
+
+#include "internal.h"
+#include "node_slots.h"
+
+using namespace FastNoise;
+using namespace FastNoise::Slots;
+
+namespace
+{
+    // exact float literal
+    std::string Lit( float v )
+    {
+        char buf[64];
+        if( std::isnan( v ) )
+        {
+            std::snprintf( buf, sizeof( buf ), "__int_as_float(0x%08x)", (unsigned)Impl::Bits( v ) );
+        }
+        else if( std::isinf( v ) )
+        {
+            std::snprintf( buf, sizeof( buf ), "%sFN2_INF", v < 0 ? "-" : "" );
+        }
+        else
+        {
+            std::snprintf( buf, sizeof( buf ), "%af", v );
+            if( v < 0 || ( v == 0 && std::signbit( v ) ) ) return std::string( "(" ) + buf + ")";
+        }
+        return buf;
+    }
+
+    std::string Int( int v )
+    {
+        char buf[32];
+        std::snprintf( buf, sizeof( buf ), v < 0 ? "(%d)" : "%d", v );
+        if( v == INT32_MIN ) return "(-2147483647 - 1)";
+        return buf;
+    }
+
+    const char* const kAxis[4] = { "x", "y", "z", "w" };
+
+    // "x, y, z"
+    std::string Pos( int dim, const char* prefix = "" )
+    {
+        std::string s;
+        for( int d = 0; d < dim; d++ )
+        {
+            if( d ) s += ", ";
+            s += prefix;
+            s += kAxis[d];
+        }
+        return s;
+    }
+
+    // "float x, float y, float z"
+    std::string PosDecl( int dim, const char* type = "float ", const char* prefix = "" )
+    {
+        std::string s;
+        for( int d = 0; d < dim; d++ )
+        {
+            if( d ) s += ", ";
+            s += type;
+            s += prefix;
+            s += kAxis[d];
+        }
+        return s;
+    }
+
+    struct Emitter
+    {
+        std::ostringstream out;
+        std::unordered_map<const Generator*, int> index;
+        std::set<std::pair<int, int>> genDone, warpDone;
+        std::string error;
+        int depth = 0;
+
+        int IndexOf( const Generator* g )
+        {
+            auto it = index.find( g );
+            if( it != index.end() ) return it->second;
+            int k = (int)index.size();
+            index.emplace( g, k );
+            return k;
+        }
+
+        void Fail( const std::string& why )
+        {
+            if( error.empty() ) error = why;
+        }
+
+        // ---------------------------------------------------------------- naming + recursion
+        std::string Gen( const Generator* g, int dim )
+        {
+            if( !g )
+            {
+                Fail( "a required source node is not set" );
+                return "fn2_missing";
+            }
+            int k = IndexOf( g );
+            if( genDone.insert( { k, dim } ).second )
+            {
+                if( ++depth > 256 )
+                {
+                    Fail( "node tree is too deep or cyclic" );
+                }
+                else
+                {
+                    std::string body = Body( g, k, dim ); // emits the children first
+                    out << "// " << g->GetMetadata().name << " " << dim << "D\n"
+                        << "FN2_DI float n" << k << "_" << dim << "( int seed, " << PosDecl( dim ) << " )\n{\n" << body << "}\n\n";
+                }
+                --depth;
+            }
+            return "n" + std::to_string( k ) + "_" + std::to_string( dim );
+        }
+
+        // call expression of a required source
+        std::string Call( const Generator* g, int dim, const std::string& seed, const std::string& pos )
+        {
+            return Gen( g, dim ) + "( " + seed + ", " + pos + " )";
+        }
+
+        std::string Src( const Generator* owner, int lookup, int dim, const std::string& seed, const std::string& pos )
+        {
+            return Call( owner->State().lookups[lookup].get(), dim, seed, pos );
+        }
+
+        // hybrid: literal or call
+        std::string Hyb( const Generator* owner, int hybrid, int dim, const std::string& seed, const std::string& pos )
+        {
+            const Impl::NodeState::Hybrid& h = owner->State().hybrids[hybrid];
+            if( h.node ) return Call( h.node.get(), dim, seed, pos );
+            return Lit( h.constant );
+        }
+
+        static bool HybIsConst( const Generator* owner, int hybrid, float value )
+        {
+            const Impl::NodeState::Hybrid& h = owner->State().hybrids[hybrid];
+            return !h.node && h.constant == value;
+        }
+
+        // ScaleOutput [BasicGenerators.inl:27-30]: fma( (1/(max-min)) * rangeScale, value - min, rangeMin ), factor folded on the host in float
+        static std::string Range( const Impl::NodeState& s, const std::string& value, float nativeMin, float nativeMax )
+        {
+            float k = ( 1.0f / ( nativeMax - nativeMin ) ) * s.f[F_RangeScale];
+            return "fn2::fma_( " + Lit( k ) + ", " + value + " - " + Lit( nativeMin ) + ", " + Lit( s.f[F_RangeMin] ) + " )";
+        }
+
+        static std::string ScalePositions( const Impl::NodeState& s, int dim )
+        {
+            std::string code;
+            for( int d = 0; d < dim; d++ ) code += std::string( "    " ) + kAxis[d] + " *= " + Lit( s.f[F_Frequency] ) + ";\n";
+            return code;
+        }
+
+        static std::string AddSeedOffset( const Impl::NodeState& s )
+        {
+            return "    seed = fn2::iadd( seed, " + Int( s.i[I_SeedOffset] ) + " );\n";
+        }
+
+        // ---------------------------------------------------------------- domain warps
+        static bool IsWarp( std::uint8_t id ) { return id == N_DomainWarpGradient || id == N_DomainWarpSimplex || id == N_DomainWarpSuperSimplex; }
+
+        // w<K>_<D>( seed, amp, scaled pos..., pos refs... ) -> strength, the reference's virtual Warp() [DomainWarp.inl:24-26]
+        std::string Warp( const Generator* g, int dim )
+        {
+            int k = IndexOf( g );
+            std::string name = "w" + std::to_string( k ) + "_" + std::to_string( dim );
+            if( !warpDone.insert( { k, dim } ).second ) return name;
+
+            const Impl::NodeState& s = g->State();
+            out << "// " << g->GetMetadata().name << "::Warp " << dim << "D\n"
+                << "FN2_DI float " << name << "( int seed, float warpAmp, " << PosDecl( dim, "float ", "s" ) << ", " << PosDecl( dim, "float& " ) << " )\n{\n";
+            if( s.nodeId == N_DomainWarpGradient )
+            {
+                out << AddSeedOffset( s ) // Warp() adds the offset itself [DomainWarp.inl:35,79,136]
+                    << "    return fn2::warp_gradient" << dim << "( seed, warpAmp, " << Pos( dim, "s" ) << ", " << Pos( dim );
+                for( int d = 0; d < dim; d++ ) out << ", " << Lit( s.f[F_K0 + d] );
+                out << " );\n";
+            }
+            else
+            {
+                Fail( std::string( g->GetMetadata().name ) + " is not implemented by this build yet" );
+                out << "    return 0.0f;\n";
+            }
+            out << "}\n\n";
+            return name;
+        }
+
+        // "sx*f, sy*f" helper for warp calls
+        static std::string Scaled( int dim, const std::string& factor, const char* prefix = "" )
+        {
+            std::string s;
+            for( int d = 0; d < dim; d++ )
+            {
+                if( d ) s += ", ";
+                s += std::string( prefix ) + kAxis[d] + " * " + factor;
+            }
+            return s;
+        }
+
+        // ---------------------------------------------------------------- per node bodies
+        std::string Body( const Generator* g, int k, int dim )
+        {
+            const Impl::NodeState& s = g->State();
+            const std::string P = Pos( dim );
+            const std::string D = std::to_string( dim );
+            std::ostringstream b;
+
+            auto cellularPrologue = [&]( bool ranged ) // common head of the three Cellular nodes [Cellular.inl:22-29]
+            {
+                (void)ranged;
+                const char* jitterK = dim == 2 ? "fn2::kJitter2D" : ( dim == 3 ? "fn2::kJitter3D" : "fn2::kJitter4D" );
+                const char* sizeK = dim == 2 ? "fn2::kSizeJitterScale2D" : ( dim == 3 ? "fn2::kSizeJitterScale3D" : "fn2::kSizeJitterScale4D" );
+                bool sizeJ = s.hybrids[2].node || s.hybrids[2].constant != 0.0f;
+                b << "    const int sourceSeed = seed;\n" << AddSeedOffset( s );
+                b << "    const float jitter = " << jitterK << " * " << Hyb( g, 1, dim, "sourceSeed", P ) << ";\n";
+                if( sizeJ ) b << "    const float sizeJitter = " << Hyb( g, 2, dim, "sourceSeed", P ) << " * " << sizeK << ";\n";
+                else b << "    const float sizeJitter = 0.0f;\n";
+                b << ScalePositions( s, dim );
+                // Minkowski exponent is sampled AT the cell delta vector [Utils.inl:330]
+                b << "    auto minkowskiP = [=]( " << PosDecl( dim, "float ", "d" ) << " ) { return " << Hyb( g, 0, dim, "sourceSeed", Pos( dim, "d" ) ) << "; };\n";
+                return sizeJ;
+            };
+
+            switch( s.nodeId )
+            {
+            case N_Constant:
+                b << "    return " << Lit( s.f[F_K0] ) << ";\n";
+                break;
+
+            case N_White:
+                b << AddSeedOffset( s ) << "    return " << Range( s, "fn2::white( seed, " + P + " )", -2147483648.f, 2147483648.f ) << ";\n";
+                break;
+
+            case N_Checkerboard:
+                b << ScalePositions( s, dim ) << "    return " << Range( s, "fn2::checkerboard( " + P + " )", 0, 2 ) << ";\n";
+                break;
+
+            case N_SineWave:
+                b << ScalePositions( s, dim ) << "    return " << Range( s, "fn2::sinewave( " + P + " )", -1, 1 ) << ";\n";
+                break;
+
+            case N_Gradient: // [BasicGenerators.inl:98-108]
+                b << "    float r = 0.0f;\n";
+                for( int d = 0; d < dim; d++ )
+                {
+                    b << "    r = fn2::fma_( " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ", " << Lit( s.f[F_K0 + d] ) << ", r );\n";
+                }
+                b << "    return r;\n";
+                break;
+
+            case N_DistanceToPoint: // [BasicGenerators.inl:115-125]
+            {
+                std::string O = Pos( dim, "o" );
+                for( int d = 0; d < dim; d++ ) b << "    const float o" << kAxis[d] << " = " << kAxis[d] << ";\n";
+                for( int d = 0; d < dim; d++ ) b << "    " << kAxis[d] << " -= " << Hyb( g, d, dim, "seed", O ) << ";\n";
+                int df = s.i[I_K0];
+                if( df < 0 || df > 5 ) df = 0; // `default:` label of the switch [Utils.inl:286]
+                b << "    return fn2::calc_distance<" << df << ", true>( " << ( df == 5 ? Hyb( g, 4, dim, "seed", P ) : "0.0f" ) << ", " << P << " );\n";
+                break;
+            }
+
+            case N_Simplex:
+            case N_SuperSimplex:
+            case N_Perlin:
+            {
+                float bound;
+                const char* fn;
+                if( s.nodeId == N_Simplex ) { fn = "simplex"; bound = dim == 2 ? 0.0261208079755306243896484375f : ( dim == 3 ? 0.030586399137973785400390625f : 0.036730043590068817138671875f ); }
+                else if( s.nodeId == N_SuperSimplex ) { fn = "supersimplex"; bound = dim == 2 ? 0.14084912836551666259765625f : ( dim == 3 ? 0.0069091119803488254547119140625f : (float)0.011310013942420482635498046875 ); }
+                else { fn = "perlin"; bound = dim == 2 ? 1.726796627044677734375f : ( dim == 3 ? (float)1.0363423824310302734375 : 1.33858621120452880859375f ); }
+                b << AddSeedOffset( s ) << ScalePositions( s, dim )
+                  << "    return " << Range( s, std::string( "fn2::" ) + fn + D + "( seed, " + P + " )", -bound, bound ) << ";\n";
+                break;
+            }
+
+            case N_Value:
+                b << AddSeedOffset( s ) << ScalePositions( s, dim )
+                  << "    return " << Range( s, "fn2::value" + D + "( seed, " + P + " )", -2147483648.f, 2147483648.f ) << ";\n";
+                break;
+
+            case N_CellularValue: // [Cellular.inl:18-292]
+            {
+                bool sizeJ = cellularPrologue( true );
+                int df = s.i[I_K0];
+                if( df < 0 || df > 5 ) df = 0;
+                int top = s.i[I_K0 + 1];
+                b << "    const int cellHash = fn2::cellular_value" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
+                  << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP );\n";
+                b << "    return " << Range( s, "fn2::cvt_f( cellHash )", -2147483648.f, 2147483648.f ) << ";\n";
+                break;
+            }
+
+            case N_CellularDistance: // [Cellular.inl:295-566]
+            {
+                bool sizeJ = cellularPrologue( true );
+                int df = s.i[I_K0];
+                if( df < 0 || df > 5 ) df = 0;
+                int i0 = s.i[I_K0 + 1], i1 = s.i[I_K0 + 2], ret = s.i[I_K0 + 3];
+                if( ret < 0 || ret > 4 ) ret = 0;
+                int top = ( df == 0 || ret != 0 ) ? std::max( i0, i1 ) : i0;
+                b << "    float dist[4];\n";
+                b << "    fn2::cellular_distance" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
+                  << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, dist );\n";
+                if( df == 0 ) // GetReturn [Cellular.inl:533-537]; with index0 == index1 the entry is normalised twice, as there
+                {
+                    b << "    dist[" << i0 << "] *= fn2::inv_sqrt( dist[" << i0 << "] );\n";
+                    b << "    dist[" << i1 << "] *= fn2::inv_sqrt( dist[" << i1 << "] );\n";
+                }
+                float jitterK = dim == 2 ? 0.437016f : ( dim == 3 ? 0.396144f : 0.366025f );
+                float maxDist = 1 + jitterK;
+                maxDist *= maxDist;
+                std::string d0 = "dist[" + std::to_string( i0 ) + "]", d1 = "dist[" + std::to_string( i1 ) + "]";
+                switch( ret )
+                {
+                case 0: b << "    return " << Range( s, d0, 0, maxDist ) << ";\n"; break;
+                case 1: b << "    return " << Range( s, "( " + d0 + " + " + d1 + " )", 0, maxDist * 2 ) << ";\n"; break;
+                case 2: b << "    return " << Range( s, "fn2::abs_( " + d0 + " - " + d1 + " )", 0, maxDist ) << ";\n"; break;
+                case 3: b << "    return " << Range( s, "( " + d0 + " * " + d1 + " )", 0, maxDist * maxDist ) << ";\n"; break;
+                case 4: b << "    return " << Range( s, "( " + d0 + " * fn2::reciprocal( " + d1 + " ) )", 0, maxDist ) << ";\n"; break;
+                }
+                break;
+            }
+
+            case N_CellularLookup: // [Cellular.inl:569-806]
+            {
+                bool sizeJ = cellularPrologue( false );
+                int df = s.i[I_K0];
+                if( df < 0 || df > 5 ) df = 0;
+                std::string C = Pos( dim, "c" );
+                b << "    float " << C << ";\n";
+                b << "    fn2::cellular_lookup" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, " << C << " );\n";
+                b << "    return " << Src( g, 0, dim, "fn2::iadd( sourceSeed, 1 )", Scaled( dim, Lit( s.f[F_Scale] ), "c" ) ) << ";\n";
+                break;
+            }
+
+            case N_FractalFBm:   // [Fractal.inl:14-36]
+            case N_FractalRidged: // [Fractal.inl:44-66]
+            {
+                const bool ridged = s.nodeId == N_FractalRidged;
+                const bool weighted = !HybIsConst( g, 1, 0.0f );
+                int octaves = s.i[I_K0];
+                std::string sample = Src( g, 0, dim, "seed", P );
+                if( ridged ) sample = "fn2::abs_( " + sample + " )";
+                b << "    const float gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                if( weighted ) b << "    const float weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    float amp = 1.0f;\n";
+                b << "    float noise = " << sample << ";\n";
+                b << "    float sum = " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
+                if( octaves > 1 )
+                {
+                    b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
+                    b << "        seed = fn2::iadd( seed, 1 );\n";
+                    // with a constant weighted strength of 0 the factor is fma( 0, t - 1, 1 ) == 1 for every finite t
+                    if( weighted ) b << "        amp *= fn2::lerp( 1.0f, " << ( ridged ? "1.0f - noise" : "( noise + 1.0f ) * 0.5f" ) << ", weightedStrength );\n";
+                    b << "        amp *= gain;\n";
+                    for( int d = 0; d < dim; d++ ) b << "        " << kAxis[d] << " *= " << Lit( s.f[F_K0] ) << ";\n";
+                    b << "        noise = " << sample << ";\n";
+                    b << "        sum += " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
+                    b << "    }\n";
+                }
+                b << "    return sum;\n";
+                break;
+            }
+
+            case N_PingPong: // [Modifiers.inl:185-201]
+                b << "    const float strength = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    float t = " << Src( g, 0, dim, "seed", P ) << " * strength;\n";
+                b << "    t -= fn2::floor_( t * 0.5f ) * 2.0f;\n";
+                b << "    return t < 1.0f ? t : 2.0f - t;\n";
+                break;
+
+            case N_DomainWarpSimplex:
+            case N_DomainWarpSuperSimplex:
+            case N_DomainWarpGradient: // DomainWarp::GenT [DomainWarp.inl:9-17]
+            {
+                std::string warp = Warp( g, dim );
+                b << "    const int sourceSeed = seed;\n" << AddSeedOffset( s );
+                b << "    const float warpAmp = " << Hyb( g, 0, dim, "sourceSeed", P ) << ";\n";
+                b << "    " << warp << "( seed, warpAmp, " << Scaled( dim, Lit( s.f[F_Frequency] ) ) << ", " << P << " );\n";
+                b << "    return " << Src( g, 0, dim, "sourceSeed", P ) << ";\n";
+                break;
+            }
+
+            case N_DomainWarpFractalProgressive: // [DomainWarpFractal.inl:9-35]
+            case N_DomainWarpFractalIndependent: // [DomainWarpFractal.inl:43-73]
+            {
+                const Generator* warpNode = s.lookups[0].get();
+                if( !warpNode || !IsWarp( warpNode->State().nodeId ) )
+                {
+                    Fail( "DomainWarpFractal needs a DomainWarp node as its source" );
+                    b << "    return 0.0f;\n";
+                    break;
+                }
+                const Impl::NodeState& ws = warpNode->State();
+                const bool independent = s.nodeId == N_DomainWarpFractalIndependent;
+                const bool weighted = !HybIsConst( g, 1, 0.0f );
+                int octaves = s.i[I_K0];
+                std::string warp = Warp( warpNode, dim );
+                std::string N = independent ? Pos( dim, "n" ) : P; // position the frequency is applied to
+                b << "    float amp = " << Hyb( warpNode, 0, dim, "seed", P ) << ";\n";
+                if( weighted ) b << "    const float weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    float freq = " << Lit( ws.f[F_Frequency] ) << ";\n";
+                b << "    int seedInc = seed;\n";
+                b << "    const float gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                if( independent ) for( int d = 0; d < dim; d++ ) b << "    const float n" << kAxis[d] << " = " << kAxis[d] << ";\n";
+                b << "    float strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
+                if( octaves > 1 )
+                {
+                    b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
+                    if( weighted ) b << "        strength = fn2::fast_length_sqrt( strength );\n";
+                    b << "        seedInc = fn2::iadd( seedInc, 1 );\n";
+                    b << "        freq *= " << Lit( s.f[F_K0] ) << ";\n";
+                    if( weighted ) b << "        amp *= fn2::lerp( 1.0f, 1.0f - strength, weightedStrength );\n";
+                    b << "        amp *= gain;\n";
+                    b << "        strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
+                    b << "    }\n";
+                }
+                b << "    (void)strength;\n";
+                b << "    return " << Src( warpNode, 0, dim, "seed", P ) << ";\n";
+                break;
+            }
+
+            case N_Add:
+                b << "    return " << Src( g, 0, dim, "seed", P ) << " + " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                break;
+            case N_Multiply:
+                b << "    return " << Src( g, 0, dim, "seed", P ) << " * " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                break;
+            case N_Min:
+                b << "    return fn2::min_( " << Src( g, 0, dim, "seed", P ) << ", " << Hyb( g, 0, dim, "seed", P ) << " );\n";
+                break;
+            case N_Max:
+                b << "    return fn2::max_( " << Src( g, 0, dim, "seed", P ) << ", " << Hyb( g, 0, dim, "seed", P ) << " );\n";
+                break;
+            case N_Subtract:
+                b << "    return " << Hyb( g, 0, dim, "seed", P ) << " - " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                break;
+            case N_Divide:
+                b << "    return fn2::div_( " << Hyb( g, 0, dim, "seed", P ) << ", " << Hyb( g, 1, dim, "seed", P ) << " );\n";
+                break;
+            case N_Modulus:
+                b << "    return fn2::modulus( " << Hyb( g, 0, dim, "seed", P ) << ", " << Hyb( g, 1, dim, "seed", P ) << " );\n";
+                break;
+
+            case N_Abs:
+                b << "    return fn2::abs_( " << Src( g, 0, dim, "seed", P ) << " );\n";
+                break;
+
+            case N_SignedSquareRoot: // [Modifiers.inl:324-335]
+                b << "    const float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    return fn2::bitsf( fn2::fbits( fn2::fast_length_sqrt( fn2::abs_( v ) ) ) | ( fn2::fbits( v ) & (int)0x80000000u ) );\n";
+                break;
+
+            case N_MinSmooth: // [Blends.inl:126-143]
+            case N_MaxSmooth: // [Blends.inl:145-162]
+            {
+                const char* neg = s.nodeId == N_MaxSmooth ? "-" : "";
+                b << "    const float a = " << neg << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const float b = " << neg << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const float smoothness = fn2::max_( 0x1p-126f, fn2::abs_( " << Hyb( g, 1, dim, "seed", P ) << " ) );\n";
+                b << "    float h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
+                b << "    h *= fn2::reciprocal( smoothness );\n";
+                b << "    return " << neg << "fn2::fnma_( " << Lit( 1.0f / 6.0f ) << ", h * h * h * smoothness, fn2::min_( a, b ) );\n";
+                break;
+            }
+
+            case N_PowFloat: // [Blends.inl:72-82]
+                b << "    const float v = fn2::max_( fn2::abs_( " << Hyb( g, 0, dim, "seed", P ) << " ), 0x1p-126f );\n";
+                b << "    return fn2::pow_pos( v, " << Hyb( g, 1, dim, "seed", P ) << " );\n";
+                break;
+
+            case N_PowInt: // [Blends.inl:84-101]
+                b << "    const float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    float p = v * v;\n";
+                b << "    for( int i = 2; i < " << Int( s.i[I_K0] ) << "; i++ ) p *= v;\n";
+                b << "    return p;\n";
+                break;
+
+            case N_DomainScale:
+                b << "    return " << Src( g, 0, dim, "seed", Scaled( dim, Lit( s.f[F_K0] ) ) ) << ";\n";
+                break;
+
+            case N_DomainOffset: // [Modifiers.inl:15-28] every offset is sampled at the un-offset position
+            {
+                std::string O = Pos( dim, "o" );
+                for( int d = 0; d < dim; d++ ) b << "    const float o" << kAxis[d] << " = " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ";\n";
+                b << "    return " << Src( g, 0, dim, "seed", O ) << ";\n";
+                break;
+            }
+
+            case N_DomainRotate: // [Modifiers.inl:30-61], matrix as Modifiers.h CalculateRotation
+            {
+                const float yc = s.f[F_K0], ys = s.f[F_K0 + 1], pc = s.f[F_K0 + 2], ps = s.f[F_K0 + 3], rc = s.f[F_K0 + 4], rs = s.f[F_K0 + 5];
+                if( dim == 4 )
+                {
+                    b << "    return " << Src( g, 0, 4, "seed", P ) << ";\n";
+                }
+                else if( dim == 2 && ps == 0.0f && rs == 0.0f )
+                {
+                    b << "    return " << Src( g, 0, 2, "seed",
+                        "fn2::fnma_( y, " + Lit( ys ) + ", x * " + Lit( yc ) + " ), fn2::fma_( x, " + Lit( ys ) + ", y * " + Lit( yc ) + " )" ) << ";\n";
+                }
+                else if( dim == 2 )
+                {
+                    b << "    return " << Gen( g, 3 ) << "( seed, x, y, 0.0f );\n";
+                }
+                else
+                {
+                    const float xa = yc * pc, xb = yc * ps * rs - ys * rc, xc = yc * ps * rc + ys * rs;
+                    const float ya = ys * pc, yb = ys * ps * rs + yc * rc, ycc = ys * ps * rc - yc * rs;
+                    const float za = -ps, zb = pc * rs, zc = pc * rc;
+                    auto row = [&]( float a, float bb, float c )
+                    {
+                        return "fn2::fma_( x, " + Lit( a ) + ", fn2::fma_( y, " + Lit( bb ) + ", z * " + Lit( c ) + " ) )";
+                    };
+                    b << "    return " << Src( g, 0, 3, "seed", row( xa, xb, xc ) + ", " + row( ya, yb, ycc ) + ", " + row( za, zb, zc ) ) << ";\n";
+                }
+                break;
+            }
+
+            case N_DomainAxisScale:
+                for( int d = 0; d < dim; d++ ) b << "    " << kAxis[d] << " *= " << Lit( s.f[F_K0 + d] ) << ";\n";
+                b << "    return " << Src( g, 0, dim, "seed", P ) << ";\n";
+                break;
+
+            case N_SeedOffset:
+                b << "    return " << Src( g, 0, dim, "fn2::iadd( seed, " + Int( s.i[I_K0] ) + " )", P ) << ";\n";
+                break;
+
+            case N_ConvertRGBA8: // [Modifiers.inl:103-127]
+            {
+                const float lo = s.f[F_K0], hi = s.f[F_K0 + 1];
+                b << "    float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    v = fn2::min_( v, " << Lit( hi ) << " );\n";
+                b << "    v = fn2::max_( v, " << Lit( lo ) << " );\n";
+                b << "    v -= " << Lit( lo ) << ";\n";
+                b << "    v *= " << Lit( 255.0f / ( hi - lo ) ) << ";\n";
+                b << "    const int byteVal = fn2::cvt_i( v );\n";
+                b << "    return fn2::bitsf( (int)0xff000000u | byteVal | fn2::shl( byteVal, 8 ) | fn2::shl( byteVal, 16 ) );\n";
+                break;
+            }
+
+            case N_GeneratorCache:
+                b << "    return " << Src( g, 0, dim, "seed", P ) << ";\n";
+                break;
+
+            case N_Fade: // [Blends.inl:164-199]
+            {
+                b << "    float fade = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const float fadeMin = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    const float fadeMax = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
+                b << "    const float fadeRange = fadeMax - fadeMin;\n";
+                b << "    fade = fn2::div_( fade - fadeMin, fadeRange );\n";
+                b << "    fade = fn2::max_( 0.0f, fn2::min_( 1.0f, fade ) );\n";
+                if( s.i[I_K0] == 1 ) b << "    fade = fn2::hermite( fade );\n";
+                if( s.i[I_K0] == 2 ) b << "    fade = fn2::quintic( fade );\n";
+                b << "    fade = fadeRange == 0.0f ? 0.5f : fade;\n";
+                b << "    return fn2::lerp( " << Src( g, 0, dim, "seed", P ) << ", " << Src( g, 1, dim, "seed", P ) << ", fade );\n";
+                break;
+            }
+
+            case N_Remap: // [Modifiers.inl:76-100]
+                b << "    const float source = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const float fromMin = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const float fromMax = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    const float toMin = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
+                b << "    const float toMax = " << Hyb( g, 3, dim, "seed", P ) << ";\n";
+                b << "    float result = toMin + ( fn2::div_( source - fromMin, fromMax - fromMin ) * ( toMax - toMin ) );\n";
+                if( s.i[I_K0] == 1 )
+                {
+                    b << "    result = fn2::max_( result, toMin );\n";
+                    b << "    result = fn2::min_( result, toMax );\n";
+                }
+                b << "    return result;\n";
+                break;
+
+            case N_Terrace: // [Modifiers.inl:130-182]
+            {
+                b << "    float source = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    source *= " << Lit( s.f[F_K0] ) << ";\n";
+                b << "    float rounded = fn2::round_( source );\n";
+                const bool dynamic = (bool)s.hybrids[0].node;
+                if( dynamic || s.hybrids[0].constant != 0.0f )
+                {
+                    if( dynamic ) b << "    const float smoothness = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                    b << "    float diff = rounded - source;\n";
+                    b << "    const bool diffSign = diff < 0.0f;\n";
+                    b << "    diff = fn2::abs_( diff );\n";
+                    b << "    diff = 0.5f - diff;\n";
+                    if( dynamic ) b << "    diff *= 1.0f + fn2::reciprocal( smoothness );\n";
+                    else b << "    diff *= " << Lit( s.f[F_K0 + 2] ) << ";\n";
+                    b << "    diff = fn2::min_( diff, 0.5f );\n";
+                    b << "    diff = diffSign ? 0.5f - diff : diff - 0.5f;\n";
+                    if( dynamic ) b << "    rounded = smoothness != 0.0f ? rounded + diff : rounded;\n";
+                    else b << "    rounded += diff;\n";
+                }
+                b << "    return rounded * " << Lit( s.f[F_K0 + 1] ) << ";\n";
+                break;
+            }
+
+            case N_AddDimension: // [Modifiers.inl:219-237]
+                if( dim == 4 ) b << "    return " << Src( g, 0, 4, "seed", P ) << ";\n";
+                else b << "    return " << Src( g, 0, dim + 1, "seed", P + ", " + Hyb( g, 0, dim, "seed", P ) ) << ";\n";
+                break;
+
+            case N_RemoveDimension: // [Modifiers.inl:239-277]
+            {
+                int removed = s.i[I_K0];
+                if( dim == 2 || removed < 0 || removed >= dim )
+                {
+                    b << "    return " << Src( g, 0, dim, "seed", P ) << ";\n";
+                }
+                else
+                {
+                    std::string kept;
+                    for( int d = 0; d < dim; d++ )
+                    {
+                        if( d == removed ) continue;
+                        if( !kept.empty() ) kept += ", ";
+                        kept += kAxis[d];
+                    }
+                    b << "    return " << Src( g, 0, dim - 1, "seed", kept ) << ";\n";
+                }
+                break;
+            }
+
+            case N_DomainRotatePlane: // [Modifiers.inl:352-409]
+            {
+                bool xz = dim != 2 && s.i[I_K0] == 1; // 2D input always uses the XY preset
+                if( dim == 2 ) b << "    const float z = 0.0f;\n";
+                const char* A = xz ? "z" : "y"; // the axis paired with x
+                const char* B = xz ? "y" : "z"; // the axis that is "improved away"
+                b << "    const float pair = x + " << A << ";\n";
+                b << "    const float s2 = pair * -0.211324865405187f;\n";
+                b << "    float nb = " << B << " * 0.577350269189626f;\n";
+                b << "    const float nx = x + s2 - nb;\n";
+                b << "    const float na = " << A << " + s2 - nb;\n";
+                b << "    nb = nb + pair * 0.577350269189626f;\n";
+                std::string rotated = xz ? "nx, nb, na" : "nx, na, nb";
+                if( dim == 4 ) rotated += ", w";
+                b << "    return " << Src( g, 0, dim == 2 ? 3 : dim, "seed", rotated ) << ";\n";
+                break;
+            }
+
+            default:
+                Fail( "unknown node id " + std::to_string( (int)s.nodeId ) );
+                b << "    return 0.0f;\n";
+            }
+            (void)k;
+            return b.str();
+        }
+    };
+
+    // ------------------------------------------------------------------ entry kernels
+    std::string GridEntry( int dim, const std::string& root, int ppt )
+    {
+        std::ostringstream k;
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::GridArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+          << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
+          << "    const bool valid = first < a.total;\n"
+          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    if( valid )\n    {\n"
+          << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
+          << "        const unsigned ix = first - rowLocal * (unsigned)a.count[0];\n"
+          << "        const unsigned row = rowLocal + a.rowBegin;\n";
+        if( dim == 2 )
+        {
+            k << "        const unsigned iy = row;\n";
+        }
+        else if( dim == 3 )
+        {
+            k << "        const unsigned iz = fn2::fast_div( row, a.divY );\n"
+              << "        const unsigned iy = row - iz * (unsigned)a.count[1];\n";
+        }
+        else
+        {
+            k << "        const unsigned plane = fn2::fast_div( row, a.divY );\n"
+              << "        const unsigned iy = row - plane * (unsigned)a.count[1];\n"
+              << "        const unsigned iw = fn2::fast_div( plane, a.divZ );\n"
+              << "        const unsigned iz = plane - iw * (unsigned)a.count[2];\n";
+        }
+        // positions exactly as Generator.inl:160-162: fma( float(index), step, offset )
+        for( int d = 1; d < dim; d++ )
+        {
+            k << "        const float p" << kAxis[d] << " = fn2::fma_( fn2::cvt_f( (int)i" << kAxis[d] << " ), a.step[" << d << "], a.off[" << d << "] );\n";
+        }
+        k << "        float v[" << ppt << "];\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
+          << "            const float px = fn2::fma_( fn2::cvt_f( (int)( ix + p ) ), a.step[0], a.off[0] );\n"
+          << "            v[p] = " << root << "( seed, " << Pos( dim, "p" ) << " );\n"
+          << "            vmin = fn2::min_( vmin, v[p] );\n"
+          << "            vmax = fn2::max_( vmax, v[p] );\n"
+          << "        }\n"
+          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
+          << "    }\n"
+          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+        return k.str();
+    }
+
+    std::string TileEntry( const std::string& root, int ppt )
+    {
+        std::ostringstream k;
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::TileArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+          << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
+          << "    const bool valid = first < a.total;\n"
+          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    if( valid )\n    {\n"
+          << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
+          << "        const unsigned ix = first - rowLocal * (unsigned)a.xSize;\n"
+          << "        const unsigned iy = rowLocal + a.rowBegin;\n"
+          // torus mapping [Generator.inl:400-406]
+          << "        const float yF = fn2::cvt_f( (int)iy ) * a.yMul;\n"
+          << "        const float py = fn2::cos_poly( yF ) * a.yFreq;\n"
+          << "        const float pw = fn2::sin_poly( yF ) * a.yFreq;\n"
+          << "        float v[" << ppt << "];\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
+          << "            const float xF = fn2::cvt_f( (int)( ix + p ) ) * a.xMul;\n"
+          << "            const float px = fn2::cos_poly( xF ) * a.xFreq;\n"
+          << "            const float pz = fn2::sin_poly( xF ) * a.xFreq;\n"
+          << "            v[p] = " << root << "( seed, px, py, pz, pw );\n"
+          << "            vmin = fn2::min_( vmin, v[p] );\n"
+          << "            vmax = fn2::max_( vmax, v[p] );\n"
+          << "        }\n"
+          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
+          << "    }\n"
+          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+        return k.str();
+    }
+
+    std::string PositionsEntry( int dim, const std::string& root, int ppt )
+    {
+        std::ostringstream k;
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::PosArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+          << "    const unsigned long long first = ( (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
+          << "    const bool valid = first < a.count;\n"
+          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    if( valid )\n    {\n"
+          << "        const bool full = first + " << ppt << "u <= a.count;\n"
+          << "        float in[" << dim << "][" << ppt << "];\n"
+          << "        float v[" << ppt << "];\n";
+        if( ppt == 4 )
+        {
+            k << "        if( full && a.vecIO )\n        {\n";
+            for( int d = 0; d < dim; d++ )
+            {
+                k << "            { const float4 t = __ldcs( reinterpret_cast<const float4*>( a.pos[" << d << "] + first ) ); in[" << d << "][0] = t.x; in[" << d << "][1] = t.y; in[" << d << "][2] = t.z; in[" << d << "][3] = t.w; }\n";
+            }
+            k << "        }\n        else\n";
+        }
+        k << "        {\n"
+          << "#pragma unroll\n"
+          << "            for( int p = 0; p < " << ppt << "; p++ )\n            {\n"
+          << "                const unsigned long long i = first + p < a.count ? first + p : a.count - 1;\n";
+        for( int d = 0; d < dim; d++ ) k << "                in[" << d << "][p] = a.pos[" << d << "][i];\n";
+        k << "            }\n        }\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n";
+        // pos = offset + array value [Generator.inl:327-330]
+        std::string args;
+        for( int d = 0; d < dim; d++ )
+        {
+            if( d ) args += ", ";
+            args += "a.off[" + std::to_string( d ) + "] + in[" + std::to_string( d ) + "][p]";
+        }
+        k << "            v[p] = " << root << "( seed, " << args << " );\n"
+          << "            if( first + p < a.count )\n            {\n"
+          << "                vmin = fn2::min_( vmin, v[p] );\n"
+          << "                vmax = fn2::max_( vmax, v[p] );\n"
+          << "            }\n"
+          << "        }\n"
+          << "        if( full )\n        {\n"
+          << "            fn2::store_points<" << ppt << ">( out + first, 0u, v, a.vecIO != 0 );\n"
+          << "        }\n        else\n        {\n"
+          << "            for( int p = 0; p < " << ppt << "; p++ ) if( first + p < a.count ) out[first + p] = v[p];\n"
+          << "        }\n"
+          << "    }\n"
+          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+        return k.str();
+    }
+}
+
+namespace FastNoise
+{
+    namespace Impl
+    {
+        LoweredProgram LowerTree( const Generator* root, int entryKind, int pointsPerThread, int mathMode )
+        {
+            LoweredProgram program;
+            program.pointsPerThread = pointsPerThread;
+            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 2 && pointsPerThread != 4 ) )
+            {
+                program.error = "invalid lowering request";
+                return program;
+            }
+
+            const int dim = EntryDims( entryKind );
+            Emitter emitter;
+            std::string rootFn = emitter.Gen( root, dim );
+            if( !emitter.error.empty() )
+            {
+                program.error = emitter.error;
+                return program;
+            }
+
+            std::ostringstream src;
+            src << "// generated by fastnoise2_b200 -- entry kind " << entryKind << ", " << pointsPerThread << " point(s) per thread, "
+                << ( mathMode ? "relaxed" : "strict" ) << " math\n"
+                << "#define FN2_RELAXED " << ( mathMode ? 1 : 0 ) << "\n"
+                << "#ifndef FN2_BLOCK\n#define FN2_BLOCK 256\n#endif\n"
+                << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP _Pragma( \"unroll 1\" )\n#endif\n"
+                << "#include \"fn2_device.cuh\"\n\n"
+                << emitter.out.str();
+
+            if( entryKind == kTileable2D ) src << TileEntry( rootFn, pointsPerThread );
+            else if( entryKind >= kPositions2D ) src << PositionsEntry( dim, rootFn, pointsPerThread );
+            else src << GridEntry( dim, rootFn, pointsPerThread );
+
+            program.source = src.str();
+            return program;
+        }
+    }
+}

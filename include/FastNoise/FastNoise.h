@@ -1,0 +1,36 @@
+// fastnoise2_b200 -- umbrella header: every node type plus the two factories
+// (reference: include/FastNoise/FastNoise.h:36-65).
+#pragma once
+#include "Utility/Config.h"
+
+#include "Generators/BasicGenerators.h"
+#include "Generators/Value.h"
+#include "Generators/Perlin.h"
+#include "Generators/Simplex.h"
+#include "Generators/Cellular.h"
+#include "Generators/Fractal.h"
+#include "Generators/DomainWarp.h"
+#include "Generators/DomainWarpSimplex.h"
+#include "Generators/DomainWarpFractal.h"
+#include "Generators/Modifiers.h"
+#include "Generators/Blends.h"
+
+namespace FastNoise
+{
+    /// Create a node with default parameters, e.g. `auto fbm = FastNoise::New<FastNoise::FractalFBm>();`
+    /// Returns an empty handle for FeatureSet::Invalid.
+    template<typename T>
+    SmartNode<T> New( FastSIMD::FeatureSet maxFeatureSet )
+    {
+        static_assert( std::is_base_of<Generator, T>::value, "New<T>: T must be a FastNoise node class, e.g. FastNoise::Simplex" );
+        if( maxFeatureSet == FastSIMD::FeatureSet::Invalid )
+        {
+            return nullptr;
+        }
+        return SmartNode<T>::FromRaw( static_cast<T*>( Impl::CreateNode( T::kNodeId ) ) );
+    }
+
+    /// Build a node tree from the string the Node Editor exports, e.g. "DQkGDA==" (FBm over Simplex).
+    /// nullptr on any malformed input; never throws.
+    FASTNOISE_API SmartNode<> NewFromEncodedNodeTree( const char* encodedNodeTreeString, FastSIMD::FeatureSet maxFeatureSet = FastSIMD::FeatureSet::Max );
+}

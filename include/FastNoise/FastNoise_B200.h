@@ -1,0 +1,91 @@
+/* fastnoise2_b200 -- device-side extension of the C ABI.
+ *
+ * The reference API (FastNoise_C.h) takes host pointers and has no notion of a device, a stream or a
+ * slab of a larger grid. These entry points expose what the B200 backend adds, with plain C types only:
+ *   - outputs / position arrays are CUDA device pointers and are written / read in place
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the calling thread's backend stream)
+ *   - uniform grids take the FULL grid description plus an integer slab [slabBegin, slabEnd) along the
+ *     outermost axis (y for 2D and tileable, z for 3D, w for 4D). Positions are derived from GLOBAL
+ *     integer indices, fma( float(index), step, offset ), exactly as the reference's single-call loop
+ *     does (Generator.inl:160-162), so N ranks each generating one slab produce bit-identical values
+ *     to one call over the whole grid. `noiseOut` points at the first element OF THE SLAB.
+ *   - min/max: `deviceMinMax` (may be NULL) is a device unsigned[2] accumulator, see fnb200MinMax*.
+ * All functions return 0 on success or a negative FNB200_E* code; fnb200LastError() has the text.
+ */
+#ifndef FASTNOISE_B200_EXT_H
+#define FASTNOISE_B200_EXT_H
+
+#include "Utility/Export.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum
+{
+    FNB200_OK = 0,
+    FNB200_EINVAL = -1,   /* bad argument (null node, negative count, empty slab ...) */
+    FNB200_ECUDA = -2,    /* CUDA runtime error (no device, launch failure, out of memory) */
+    FNB200_ECOMPILE = -3, /* NVRTC rejected the generated program */
+    FNB200_EUNSUPPORTED = -4 /* tree contains a node type this build cannot lower */
+};
+
+/* Thread-local description of the last failure in this library ("" if none). */
+FASTNOISE_API const char* fnb200LastError( void );
+
+/* 1 if a usable CUDA device (compute capability 10.x) and NVRTC are present. Never throws. */
+FASTNOISE_API int fnb200DeviceAvailable( void );
+
+/* Numerics mode for trees compiled AFTER the call (process-wide):
+ *   0 = strict  : no FMA contraction beyond the reference's explicit FMulAdd sites, IEEE div/sqrt (default; parity mode)
+ *   1 = relaxed : nvcc FMA contraction on, approximate rsqrt/rcp where the reference's RELAXED build uses them */
+FASTNOISE_API int fnb200SetMathMode( int mode );
+FASTNOISE_API int fnb200GetMathMode( void );
+
+/* Lower + compile the tree for one entry kind ahead of time (otherwise done on first use).
+ * kind: 2,3,4 = uniform grid 2D/3D/4D; 5 = tileable 2D; 12,13,14 = position array 2D/3D/4D. */
+FASTNOISE_API int fnb200Prepare( const void* node, int kind );
+
+/* Copies the generated CUDA source of (node, kind) into buf (NUL-terminated, truncated to bufSize); returns full length. */
+FASTNOISE_API long fnb200GetKernelSource( const void* node, int kind, char* buf, long bufSize );
+
+/* Min/max accumulator helpers. The accumulator is two unsigned ints in device memory holding
+ * order-preserving encodings of -min and +max; zero bytes = empty. Decode after the stream is idle. */
+FASTNOISE_API int fnb200MinMaxReset( void* deviceMinMax, void* stream );
+FASTNOISE_API int fnb200MinMaxRead( const void* deviceMinMax, void* stream, float* outputMinMax /* float[2] */ );
+
+FASTNOISE_API int fnb200GenUniformGrid2D( const void* node, float* deviceOut, float xOffset, float yOffset, int xCount, int yCount,
+                                          float xStepSize, float yStepSize, int seed, int slabBegin, int slabEnd,
+                                          void* deviceMinMax, void* stream );
+FASTNOISE_API int fnb200GenUniformGrid3D( const void* node, float* deviceOut, float xOffset, float yOffset, float zOffset,
+                                          int xCount, int yCount, int zCount, float xStepSize, float yStepSize, float zStepSize,
+                                          int seed, int slabBegin, int slabEnd, void* deviceMinMax, void* stream );
+FASTNOISE_API int fnb200GenUniformGrid4D( const void* node, float* deviceOut, float xOffset, float yOffset, float zOffset, float wOffset,
+                                          int xCount, int yCount, int zCount, int wCount,
+                                          float xStepSize, float yStepSize, float zStepSize, float wStepSize,
+                                          int seed, int slabBegin, int slabEnd, void* deviceMinMax, void* stream );
+FASTNOISE_API int fnb200GenTileable2D( const void* node, float* deviceOut, int xSize, int ySize, float xStepSize, float yStepSize,
+                                       int seed, int slabBegin, int slabEnd, void* deviceMinMax, void* stream );
+/* dims = 2, 3 or 4; unused position arrays may be NULL. `count` positions starting at the given pointers. */
+FASTNOISE_API int fnb200GenPositionArray( const void* node, int dims, float* deviceOut, long long count,
+                                          const float* xPos, const float* yPos, const float* zPos, const float* wPos,
+                                          float xOffset, float yOffset, float zOffset, float wOffset,
+                                          int seed, void* deviceMinMax, void* stream );
+
+/* Synthetic input for the position-array benchmark: fills out[i] (device) with uniform floats in
+ * [lo, hi) from Philox4x32-10( key, counter = firstIndex + i, stream id = axis ). Reproducible on any rank. */
+FASTNOISE_API int fnb200FillUniformPhilox( float* deviceOut, long long count, long long firstIndex, unsigned key, unsigned axis,
+                                           float lo, float hi, void* stream );
+
+/* ALU roofline probe: runs `iters` rounds of independent FFMA / IMAD / LOP3 (mode 0/1/2) or a 50:50
+ * FFMA+LOP3 mix (mode 3) on every SM and returns achieved lane-ops per second (0 on failure). */
+FASTNOISE_API double fnb200MeasureAluPeak( int mode, int iters );
+
+/* Number of kernels this library has launched in the calling process (all threads). */
+FASTNOISE_API unsigned long long fnb200LaunchCount( void );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
