@@ -77,6 +77,7 @@ PROTOTYPES = {
     "fnb200GenPositionArray": (I, [P, I, P, LL, P, P, P, P, F, F, F, F, I, P, P]),
     "fnb200FillUniformPhilox": (I, [P, LL, LL, U, U, F, F, P]),
     "fnb200MeasureAluPeak": (ctypes.c_double, [I, I]),
+    "fnb200CanonicalEncodedNodeTree": (ctypes.c_long, [S, P, ctypes.c_long]),
     "fnb200LaunchCount": (ctypes.c_ulonglong, []),
 }
 

@@ -9,6 +9,9 @@
 
 #include <cuda_runtime_api.h>
 #include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
 
 #include "backend.h"
 
@@ -232,7 +235,8 @@ extern "C"
         return (long)source.size();
     }
 
-    static cudaStream_t StreamOf( void* stream ) { return stream ? (cudaStream_t)stream : Impl::ThreadStream(); }
+    // NULL is CUDA's default (legacy) stream, as everywhere else in CUDA; torch's default stream is that stream too
+    static cudaStream_t StreamOf( void* stream ) { return (cudaStream_t)stream; }
 
     static int CudaRc( cudaError_t e, const char* what )
     {
@@ -355,6 +359,20 @@ extern "C"
     {
         if( !deviceOut || count < 0 ) return FNB200_EINVAL;
         return Impl::FillUniformPhilox( deviceOut, count, firstIndex, key, axis, lo, hi, StreamOf( stream ) );
+    }
+
+    long fnb200CanonicalEncodedNodeTree( const char* encodedString, char* buf, long bufSize )
+    {
+        std::vector<std::unique_ptr<NodeData>> records;
+        NodeData* root = Metadata::DeserialiseNodeData( encodedString, records );
+        std::string text = root ? Metadata::SerialiseNodeData( root, false ) : std::string();
+        if( buf && bufSize > 0 )
+        {
+            long n = std::min<long>( bufSize - 1, (long)text.size() );
+            std::memcpy( buf, text.data(), (size_t)n );
+            buf[n] = 0;
+        }
+        return (long)text.size();
     }
 
     double fnb200MeasureAluPeak( int mode, int iters ) { return Impl::MeasureAluPeak( mode, iters ); }

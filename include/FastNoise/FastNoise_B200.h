@@ -3,7 +3,7 @@
  * The reference API (FastNoise_C.h) takes host pointers and has no notion of a device, a stream or a
  * slab of a larger grid. These entry points expose what the B200 backend adds, with plain C types only:
  *   - outputs / position arrays are CUDA device pointers and are written / read in place
- *   - `stream` is a cudaStream_t passed as void* (NULL = the calling thread's backend stream)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = CUDA's default stream); calls only enqueue work and return
  *   - uniform grids take the FULL grid description plus an integer slab [slabBegin, slabEnd) along the
  *     outermost axis (y for 2D and tileable, z for 3D, w for 4D). Positions are derived from GLOBAL
  *     integer indices, fma( float(index), step, offset ), exactly as the reference's single-call loop
@@ -80,6 +80,11 @@ FASTNOISE_API int fnb200FillUniformPhilox( float* deviceOut, long long count, lo
 /* ALU roofline probe: runs `iters` rounds of independent FFMA / IMAD / LOP3 (mode 0/1/2) or a 50:50
  * FFMA+LOP3 mix (mode 3) on every SM and returns achieved lane-ops per second (0 on failure). */
 FASTNOISE_API double fnb200MeasureAluPeak( int mode, int iters );
+
+/* Decodes `encodedString` into NodeData records (Metadata::DeserialiseNodeData) and serialises them again
+ * (Metadata::SerialiseNodeData): the canonical spelling of a tree. Writes a NUL-terminated string into buf
+ * (truncated to bufSize) and returns its full length, 0 if the input does not decode. */
+FASTNOISE_API long fnb200CanonicalEncodedNodeTree( const char* encodedString, char* buf, long bufSize );
 
 /* Number of kernels this library has launched in the calling process (all threads). */
 FASTNOISE_API unsigned long long fnb200LaunchCount( void );

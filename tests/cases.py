@@ -1,0 +1,67 @@
+"""Shared case tables: the golden cases (small enough to commit) and the SURVEY.md 8c smoke table."""
+import numpy as np
+
+from fastnoise2_b200.api import TREES
+
+DEMO_TREES = {
+    # shipped with the reference's Node Editor (tools/NodeEditor/util/DemoNodeTrees.inl:5-6): written by the REAL encoder
+    "mountain_terrain": "E@BBZEG@BD8JFgIECArXIzwECiQIw/UoPwkuAAE@BJDQAH@BC@AIEAJBw@ABZEED0KV78YZmZmPwQDmpkZPwsAAIA/HAMAAHBCBA==",
+    "cellular_caves": "FgIcCS4AAQ@BklCQs@BlRBDNzMw9G@AIMAgAw@ADgC@BCiQIzczMPgkJ@BPkIQH4XrPhjNzEw/DBIkCM3MzD4JCQ@ADBCCAE@BQzczMvhg@B/JAL/BAAL7FE4PgQKFwkNCQg@CQQQDuB4FPwt7FC4/BAOPwnU8DA==",
+}
+
+# checksums of the survey's prototype strict oracle (scalar 4-lane, libm) -- an independent
+# build of the same semantics. call = (kind, args): grid3d 64^3 step 4, grid2d 512^2 step 1, grid4d 32,32,16,16 step 4; seed 1337
+SURVEY_SMOKE = {
+    "fbm_simplex_readme": ("grid2d", "15866cbf", -1.597328, 1.550798),
+    "c1_simplex": ("grid3d", "9e65503f", -0.996678, 0.999883),
+    "c2_fbm5_perlin": ("grid2d", "7cda0d2b", -1.058768, 1.075703),
+    "c3a_cellular_distance": ("grid3d", "23156f56", -0.999909, -0.135814),
+    "c3b_cellular_lookup_white": ("grid3d", "e3ae3be6", -0.983556, 0.968467),
+    "c5_supersimplex": ("grid4d", "d9cee143", -0.790859, 0.796379),
+    "c4_terrain": ("grid3d", "be4f2cf0", 0.166667, 0.928188),
+    "cellular_caves": ("grid3d", "06837b6b", -2.118493, 0.076068),
+    "mountain_terrain": ("grid3d", "40043e0d", -0.372797, 2.460488),
+}
+
+
+def survey_call(kind):
+    if kind == "grid2d":
+        return dict(kind="grid2d", off=(0.0, 0.0), n=(512, 512), step=(1.0, 1.0), seed=1337)
+    if kind == "grid3d":
+        return dict(kind="grid3d", off=(0.0, 0.0, 0.0), n=(64, 64, 64), step=(4.0, 4.0, 4.0), seed=1337)
+    return dict(kind="grid4d", off=(0.0, 0.0, 0.0, 0.0), n=(32, 32, 16, 16), step=(4.0, 4.0, 4.0, 4.0), seed=1337)
+
+
+def golden_positions(n, dims, seed=1337):
+    rng = np.random.default_rng(seed)
+    return [rng.uniform(-1000.0, 1000.0, n).astype(np.float32) for _ in range(dims)]
+
+
+GOLDEN_CASES = {
+    "c1_simplex_grid3d": dict(tree=TREES["c1_simplex"], kind="grid3d", off=(-5.3, 2.1, 0.7), n=(28, 24, 20), step=(3.7, 3.7, 3.7), seed=1337),
+    "c2_fbm5_perlin_grid2d": dict(tree=TREES["c2_fbm5_perlin"], kind="grid2d", off=(-17.0, 4.5), n=(96, 80), step=(0.25, 0.25), seed=1337),
+    "c2_fbm5_perlin_tileable": dict(tree=TREES["c2_fbm5_perlin"], kind="tileable2d", n=(72, 56), step=(1.0, 1.0), seed=1337),
+    "c3a_cellular_distance_grid3d": dict(tree=TREES["c3a_cellular_distance"], kind="grid3d", off=(0.0, 0.0, 0.0), n=(24, 24, 20), step=(5.1, 5.1, 5.1), seed=1337),
+    "c3b_cellular_lookup_white_grid3d": dict(tree=TREES["c3b_cellular_lookup_white"], kind="grid3d", off=(0.0, 0.0, 0.0), n=(24, 24, 20), step=(5.1, 5.1, 5.1), seed=1337),
+    "c3c_cellular_lookup_gradient_grid3d": dict(tree=TREES["c3c_cellular_lookup_gradient"], kind="grid3d", off=(0.0, 0.0, 0.0), n=(24, 24, 20), step=(5.1, 5.1, 5.1), seed=1337),
+    "c4_terrain_grid3d": dict(tree=TREES["c4_terrain"], kind="grid3d", off=(0.0, 0.0, 0.0), n=(28, 24, 20), step=(6.3, 6.3, 6.3), seed=1337),
+    "c5_supersimplex_pos4d": dict(tree=TREES["c5_supersimplex"], kind="pos4d", count=4099, off=(0.0, 0.0, 0.0, 0.0), seed=1337),
+    "cellular_caves_grid3d": dict(tree=DEMO_TREES["cellular_caves"], kind="grid3d", off=(1.0, -2.0, 3.0), n=(20, 20, 16), step=(2.9, 2.9, 2.9), seed=-7),
+    "fbm_simplex_grid4d": dict(tree=TREES["fbm_simplex_readme"], kind="grid4d", off=(0.5, 0.25, -0.75, 9.0), n=(12, 10, 8, 6), step=(7.0, 7.0, 7.0, 7.0), seed=0x7fffffff),
+}
+
+
+def run_case(node, case):
+    """node: anything with grid2d/grid3d/grid4d/tileable2d/positions methods returning (out, minmax) -- tests.helpers.RefNode,
+    tests.helpers.PortNode or the product adapter in tests.helpers.ProductNode."""
+    k = case["kind"]
+    if k == "grid2d":
+        return node.grid2d(*case["off"], *case["n"], *case["step"], case["seed"])
+    if k == "grid3d":
+        return node.grid3d(*case["off"], *case["n"], *case["step"], case["seed"])
+    if k == "grid4d":
+        return node.grid4d(*case["off"], *case["n"], *case["step"], case["seed"])
+    if k == "tileable2d":
+        return node.tileable2d(*case["n"], *case["step"], case["seed"])
+    dims = int(k[3])
+    return node.positions(golden_positions(case["count"], dims), case["off"][:dims], case["seed"])
