@@ -139,3 +139,70 @@ def load_golden():
     summary = json.load(open(os.path.join(golden_dir, "summary.json")))
     metadata = json.load(open(os.path.join(golden_dir, "metadata.json")))
     return outputs, summary, metadata
+
+
+def load_port():
+    """oracle/libfn2oracle.so: the plain-C restatement (oracle/fn2_oracle.c). None if not built."""
+    path = os.path.join(ROOT, "oracle", "libfn2oracle.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    P, I, F, LL = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+    lib.fn2oDecode.restype = P
+    lib.fn2oDecode.argtypes = [ctypes.c_char_p]
+    lib.fn2oFree.argtypes = [P]
+    lib.fn2oSupported.argtypes = [P]
+    lib.fn2oNodeId.argtypes = [P]
+    lib.fn2oGrid.argtypes = [P, P, I, P, P, P, I, LL, LL, P]
+    lib.fn2oTileable.argtypes = [P, P, I, I, F, F, I, I, I, P]
+    lib.fn2oPositions.argtypes = [P, P, I, LL, P, P, P, P, P, I, P]
+    return lib
+
+
+class PortNode:
+    """Same call surface as RefNode over the C restatement; `rows=(begin, count)` evaluates a slab with global indices."""
+
+    def __init__(self, lib, encoded):
+        self.lib = lib
+        self.handle = lib.fn2oDecode(encoded.encode())
+        self.supported = bool(self.handle) and bool(lib.fn2oSupported(self.handle))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.fn2oFree(self.handle)
+
+    def _grid(self, dims, off, n, step, seed, rows=None):
+        total_rows = int(np.prod(n[1:])) if dims > 1 else 1
+        begin, count = rows if rows else (0, total_rows)
+        out = np.empty(count * n[0], np.float32)
+        mm = np.zeros(2, np.float32)
+        offs = np.array(list(off) + [0.0] * (4 - dims), np.float32)
+        ns = np.array(list(n) + [1] * (4 - dims), np.int32)
+        steps = np.array(list(step) + [0.0] * (4 - dims), np.float32)
+        self.lib.fn2oGrid(self.handle, out.ctypes.data, dims, offs.ctypes.data, ns.ctypes.data, steps.ctypes.data, seed, begin, count, mm.ctypes.data)
+        return out, mm
+
+    def grid2d(self, x0, y0, nx, ny, sx, sy, seed, rows=None):
+        return self._grid(2, (x0, y0), (nx, ny), (sx, sy), seed, rows)
+
+    def grid3d(self, x0, y0, z0, nx, ny, nz, sx, sy, sz, seed, rows=None):
+        return self._grid(3, (x0, y0, z0), (nx, ny, nz), (sx, sy, sz), seed, rows)
+
+    def grid4d(self, x0, y0, z0, w0, nx, ny, nz, nw, sx, sy, sz, sw, seed, rows=None):
+        return self._grid(4, (x0, y0, z0, w0), (nx, ny, nz, nw), (sx, sy, sz, sw), seed, rows)
+
+    def tileable2d(self, nx, ny, sx, sy, seed, rows=None):
+        begin, count = rows if rows else (0, ny)
+        out = np.empty(count * nx, np.float32)
+        mm = np.zeros(2, np.float32)
+        self.lib.fn2oTileable(self.handle, out.ctypes.data, nx, ny, sx, sy, seed, begin, count, mm.ctypes.data)
+        return out, mm
+
+    def positions(self, pos, offsets, seed):
+        n = len(pos[0])
+        out = np.empty(n, np.float32)
+        mm = np.zeros(2, np.float32)
+        p = [a.ctypes.data for a in pos] + [None] * (4 - len(pos))
+        offs = np.array(list(offsets) + [0.0] * (4 - len(offsets)), np.float32)
+        self.lib.fn2oPositions(self.handle, out.ctypes.data, len(pos), n, p[0], p[1], p[2], p[3], offs.ctypes.data, seed, mm.ctypes.data)
+        return out, mm

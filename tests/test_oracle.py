@@ -57,3 +57,51 @@ def test_port_oracle_reproduces_golden_vectors():
         assert float(mm[0]) == summary[name]["min"] and float(mm[1]) == summary[name]["max"], name
         checked += 1
     assert checked >= 8
+
+
+def test_test_encoder_matches_known_strings(fn):
+    from tests.encode import N
+    assert N("FractalFBm", {}, [N("Simplex")]).encode() == "DQkGDA=="                      # FastNoise.h:53
+    assert N("FractalFBm", {"Octaves": 5}, [N("Perlin")]).encode() == fn.TREES["c2_fbm5_perlin"]
+    assert N("CellularLookup", {}, [N("White")]).encode() == fn.TREES["c3b_cellular_lookup_white"]
+    c4 = N("DomainWarpFractalProgressive", {}, [N("DomainWarpGradient", {"Feature Scale": 200.0}, [
+        N("Terrace", {"Step Count": 12.0}, [N("Remap", {"Clamp Output": 1}, [N("MaxSmooth", {}, [
+            N("FractalFBm", {"Octaves": 5}, [N("Simplex", {"Feature Scale": 150.0})])],
+            {"RHS": N("FractalRidged", {"Octaves": 4}, [N("Perlin", {"Feature Scale": 90.0, "Seed Offset": 7})]), "Smoothness": 0.2})],
+            {"From Max": 2.0})], {"Smoothness": 0.25})], {"Warp Amplitude": 30.0})])
+    assert c4.encode() == fn.TREES["c4_terrain"]
+
+
+def test_port_oracle_vs_strict_ref_every_node(ref):
+    """The C restatement against the reference's own sources, every node type it covers, 2D/3D/4D, constant and generated hybrids."""
+    from tests.encode import default_tree
+    port = helpers.load_port()
+    if port is None:
+        pytest.skip("oracle/libfn2oracle.so not built")
+    checked = 0
+    for hybrid_nodes in (False, True):
+        for node_id in range(47):
+            if node_id in (16, 17):
+                continue
+            text = default_tree(node_id, hybrid_nodes).encode()
+            a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
+            assert a.supported, node_id
+            for got, want in ((a.grid2d(-3.3, 2.1, 40, 40, 1.9, 1.9, 1337)[0], b.grid2d(-3.3, 2.1, 40, 40, 1.9, 1.9, 1337)[0]),
+                              (a.grid3d(-3.3, 2.1, 0.7, 14, 14, 14, 1.9, 1.9, 1.9, 1337)[0], b.grid3d(-3.3, 2.1, 0.7, 14, 14, 14, 1.9, 1.9, 1.9, 1337)[0]),
+                              (a.grid4d(-3.3, 2.1, 0.7, -1.9, 7, 7, 7, 7, 1.9, 1.9, 1.9, 1.9, 1337)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 7, 7, 7, 7, 1.9, 1.9, 1.9, 1.9, 1337)[0])):
+                same = np.array_equal(got.view(np.uint32), want.view(np.uint32)) or (np.isnan(got).all() and np.isnan(want).all())
+                assert same, (node_id, hybrid_nodes, helpers.compare(got, want))
+                checked += 1
+    assert checked == 45 * 2 * 3
+
+
+def test_port_oracle_slab_rows_equal_whole_grid():
+    port = helpers.load_port()
+    if port is None:
+        pytest.skip("oracle/libfn2oracle.so not built")
+    from fastnoise2_b200.api import TREES
+    node = helpers.PortNode(port, TREES["c4_terrain"])
+    whole, mm = node.grid3d(0.0, 0.0, 0.0, 12, 10, 9, 3.3, 3.3, 3.3, 1337)
+    parts = [node.grid3d(0.0, 0.0, 0.0, 12, 10, 9, 3.3, 3.3, 3.3, 1337, rows=(z0 * 10, (z1 - z0) * 10)) for z0, z1 in ((0, 4), (4, 5), (5, 9))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), whole.view(np.uint32))
+    assert min(p[1][0] for p in parts) == mm[0] and max(p[1][1] for p in parts) == mm[1]
