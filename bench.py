@@ -359,6 +359,11 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
+    traffic = None
+    try:  # DRAM bytes per launch of this workload's kernel from the committed `ncu --set full` capture (never measured under a timer)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     achieved = w["ops"] * points / (kernel_ms * 1e-3) / 1e12
     peak = alu_peak / 1e12
     store_gbs = out_bytes / (kernel_ms * 1e-3) / 1e9
@@ -372,7 +377,8 @@ def main():
                    "math": args.math, "l2": "output per step (%d MiB) exceeds L2; no inputs are re-read" % (out_bytes >> 20),
                    "output_minmax": [lo, hi]},
         "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "kernel": "fn2_entry (NVRTC-specialised tree kernel)", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)" if traffic else None,
+                     "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-specialised tree kernel)", "kernel_ms": kernel_ms,
                      "ops_per_point": w["ops"], "peak_source": "FFMA issue rate measured live by fnb200MeasureAluPeak (148 SM x 128 lanes x clock); MEASURED_PEAKS.json has no ALU entry",
                      "hbm_store": {"achieved_gbs": store_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": store_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                    "algorithmic_bytes_per_point": 4 + (16 if kind == "pos4d" else 0)}},

@@ -1,0 +1,64 @@
+"""Extracts the judged numbers from ncu reports brought back in gpurun_out/ into profiles/ (tracked).
+
+    python profiles/summarize_ncu.py r1 gpurun_out/prof_c4.ncu-rep:c4 gpurun_out/prof_c1.ncu-rep:c1 ...
+
+Writes profiles/<round>_ncu_summary.json (read by bench.py for roofline.traffic) and profiles/<round>_ncu_summary.md.
+"""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+    "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+]
+UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}
+
+
+def read_report(path):
+    text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(text[text.index('"ID"'):])))
+    header, units, values = rows[0], rows[1], rows[2]
+    out = {"kernel": values[header.index("Kernel Name")]}
+    for name in METRICS:
+        if name in header:
+            i = header.index(name)
+            v = float(values[i].replace(",", ""))
+            out[name] = v * UNIT_SCALE.get(units[i], 1)
+    return out
+
+
+def main():
+    tag = sys.argv[1]
+    here = os.path.dirname(os.path.abspath(__file__))
+    summary = {}
+    for arg in sys.argv[2:]:
+        path, workload = arg.rsplit(":", 1)
+        summary[workload] = read_report(path)
+        summary[workload]["dram_bytes_per_launch"] = summary[workload].get("dram__bytes_read.sum", 0) + summary[workload].get("dram__bytes_write.sum", 0)
+    json.dump(summary, open(os.path.join(here, "%s_ncu_summary.json" % tag), "w"), indent=1)
+    lines = ["# ncu --set full --clock-control none, kernel fn2_entry (one launch per workload), round %s" % tag, "",
+             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | tensor % | warp-inst | DRAM read | DRAM write | local ld/st |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for w, m in summary.items():
+        lines.append("| %s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.3g | %.3g B | %.3g B | %d/%d |" % (
+            w, m["gpu__time_duration.sum"] * 1e3, m["launch__registers_per_thread"], m["sm__warps_active.avg.pct_of_peak_sustained_active"],
+            m["smsp__issue_active.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
+            m["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"],
+            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["smsp__inst_executed.sum"], m.get("dram__bytes_read.sum", 0),
+            m.get("dram__bytes_write.sum", 0), m.get("sass__inst_executed_local_loads", 0), m.get("sass__inst_executed_local_stores", 0)))
+    open(os.path.join(here, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
