@@ -828,7 +828,7 @@ namespace FastNoise
                 << ( mathMode ? "relaxed" : "strict" ) << " math\n"
                 << "#define FN2_RELAXED " << ( mathMode ? 1 : 0 ) << "\n"
                 << "#ifndef FN2_BLOCK\n#define FN2_BLOCK 256\n#endif\n"
-                << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP _Pragma( \"unroll 1\" )\n#endif\n"
+                << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP\n#endif\n"
                 << "#include \"fn2_device.cuh\"\n\n"
                 << emitter.out.str();
 
