@@ -14,8 +14,10 @@ namespace fn2
     // base +- prime, by sign mask [Simplex.inl:475 and siblings]
     FN2_DI i32 step_prime( i32 base, i32 prime, bool negative ) { return iadd( base, negative ? isub( 0, prime ) : prime ); }
 
+    // Vertex producers shared with DomainWarpSuperSimplex [DomainWarpSimplex.inl:1133-1833 repeats the geometry below],
+    // vertices in the reference's accumulation order, falloff already raised to the 4th power.
     // [Simplex.inl:293-377]
-    FN2_DI float supersimplex2( i32 seed, float x, float y )
+    FN2_DI void supersimplex2_vertices( i32 seed, float x, float y, Verts2 ( &v )[4] )
     {
         constexpr double kSkew2 = 1.0 / ( kRoot3 + 1.0 );
         constexpr double kUnskew2 = -1.0 / ( kRoot3 + 3.0 );
@@ -35,16 +37,11 @@ namespace fn2
         float unskewDelta = (float)kUnskew2 * ( dxS + dyS );
         float dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
 
-        float falloffBase0, value;
-        { // vertex <0,0>
-            float g = grad_dot2( hash_primes( seed, xP, yP ), dxBase, dyBase );
-            falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
-            value = pow4( falloffBase0 ) * g;
-        }
+        float falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
+        v[0] = { hash_primes( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
         { // vertex <1,1>
-            float g = grad_dot2( hash_primes( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ) );
             float falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
-            value = fma_( pow4( falloff ), g, value );
+            v[1] = { hash_primes( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
         }
 
         float xyDelta = forwardXY ? (float)( kUnskew2 + 1 ) : (float)( -kUnskew2 );
@@ -57,9 +54,8 @@ namespace fn2
             i32 yv = forwardXY ? iadd( yP, kPY ) : yP;
             float dx = dxBase - ( forwardX ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
             float dy = forwardX ? dyBase - (float)( 2 * kUnskew2 ) : dyBase;
-            float g = grad_dot2( hash_primes( seed, xv, yv ), dx, dy );
             float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            value = fma_( pow4( falloff ), g, value );
+            v[2] = { hash_primes( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
         { // vertex <0,1> or <0,-1> or <2,1>
             i32 xv = forwardXY ? iadd( xP, kPX ) : xP;
@@ -67,15 +63,23 @@ namespace fn2
             yv = forwardXY ? yv : isub( yv, kPY );
             float dx = forwardY ? dxBase - (float)( 2 * kUnskew2 ) : dxBase;
             float dy = dyBase - ( forwardY ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
-            float g = grad_dot2( hash_primes( seed, xv, yv ), dx, dy );
             float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            value = fma_( pow4( falloff ), g, value );
+            v[3] = { hash_primes( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
+    }
+
+    FN2_DI float supersimplex2( i32 seed, float x, float y )
+    {
+        Verts2 v[4];
+        supersimplex2_vertices( seed, x, y, v );
+        float value = v[0].falloff * grad_dot2( v[0].hash, v[0].dx, v[0].dy );
+#pragma unroll
+        for( int k = 1; k < 4; k++ ) value = fma_( v[k].falloff, grad_dot2( v[k].hash, v[k].dx, v[k].dy ), value );
         return value;
     }
 
     // [Simplex.inl:379-576]
-    FN2_DI float supersimplex3( i32 seed, float x, float y, float z )
+    FN2_DI void supersimplex3_vertices( i32 seed, float x, float y, float z, Verts3 ( &v )[8] )
     {
         constexpr double kSkew3 = 1.0 / 3.0;
         constexpr double kReflectUnskew3 = -1.0 / 2.0;
@@ -126,75 +130,76 @@ namespace fn2
         float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud;
         float coordSum = (float)( 1 + 3 * kReflectUnskew3 ) * sum;
 
-        float value, stemA, stemB;
+        float stemA, stemB;
         { // <0,0,0>
-            float g = grad_dot3( hash_primes( seed, xP, yP, zP ), dxB, dyB, dzB );
             float fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            value = sq2( fb ) * g;
+            v[0] = { hash_primes( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
         }
         { // <1,1,1> or <-1,-1,-1>
             bool sm = xyzN < 0.0f;
             i32 sign = signbit_if( sm );
             float o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
-            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o );
             float fb = max_( fma_( o, coordSum, stemA ), 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[1] = { hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
         }
         { // <1,1,0> or <-1,-1,0>
             bool sm = xyzN < zN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0 );
             float fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[2] = { hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
         }
         { // <1,0,1> or <-1,0,-1>
             bool sm = xyzN < yN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB );
             float fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[3] = { hash_primes( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
         }
         { // <0,1,1> or <0,-1,-1>
             bool sm = xyzN < xN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float g = grad_dot3( hash_primes( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB );
             float fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[4] = { hash_primes( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
         }
         { // <1,0,0> or <-1,0,0>
             bool sm = xN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
-            float g = grad_dot3( hash_primes( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0 );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[5] = { hash_primes( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
         }
         { // <0,1,0> or <0,-1,0>
             bool sm = yN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
-            float g = grad_dot3( hash_primes( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0 );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[6] = { hash_primes( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
         }
         { // <0,0,1> or <0,0,-1>
             bool sm = zN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
-            float g = grad_dot3( hash_primes( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0 );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
-            value = fma_( sq2( fb ), g, value );
+            v[7] = { hash_primes( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
         }
+    }
+
+    FN2_DI float supersimplex3( i32 seed, float x, float y, float z )
+    {
+        Verts3 v[8];
+        supersimplex3_vertices( seed, x, y, z, v );
+        float value = v[0].falloff * grad_dot3( v[0].hash, v[0].dx, v[0].dy, v[0].dz );
+#pragma unroll
+        for( int k = 1; k < 8; k++ ) value = fma_( v[k].falloff, grad_dot3( v[k].hash, v[k].dx, v[k].dy, v[k].dz ), value );
         return value;
     }
 
     // [Simplex.inl:578-936]
-    FN2_DI float supersimplex4( i32 seed, float x, float y, float z, float w )
+    FN2_DI void supersimplex4_vertices( i32 seed, float x, float y, float z, float w, Verts4 ( &v )[16] )
     {
         constexpr double kSkew4 = 1.0 / ( kRoot5 + 1.0 );
         constexpr double kUnskew4 = -1.0 / ( kRoot5 + 5.0 );
@@ -258,48 +263,55 @@ namespace fn2
         float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud, dwB = dwS + ud;
         float coordSum = (float)( 1 + 4 * kUnskew4 ) * sum;
 
-        float value, stemA, stemB;
+        float stemA, stemB;
         { // <0,0,0,0>
-            float g = grad_dot4( hash_primes( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB );
             float fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            value = sq2( fb ) * g;
+            v[0] = { hash_primes( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
         }
 
         // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many.
         // Coordinates on stepping axes use offset1 = (K*u + 1)^sign, the others offset0 = (K*u)^sign. FALLOFF is
         // the vertex-class specific falloff base expression [Simplex.inl:692-931].
-#define FN2_SS4_VERTEX( COND, MX, MY, MZ, MW, K, FALLOFF ) \
+#define FN2_SS4_VERTEX( SLOT, COND, MX, MY, MZ, MW, K, FALLOFF ) \
         { \
             bool sm = COND; \
             i32 sign = signbit_if( sm ); \
             float o1 = fxor( (float)( K * kUnskew4 + 1 ), sign ); \
             float o0 = fxor( (float)( K * kUnskew4 ), sign ); \
             (void)o0; \
-            float g = grad_dot4( hash_primes( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
-                                              MZ ? step_prime( zP, kPZ, sm ) : zP, MW ? step_prime( wP, kPW, sm ) : wP ), \
-                                 dxB - ( MX ? o1 : o0 ), dyB - ( MY ? o1 : o0 ), dzB - ( MZ ? o1 : o0 ), dwB - ( MW ? o1 : o0 ) ); \
             float fb = max_( FALLOFF, 0.0f ); \
-            value = fma_( sq2( fb ), g, value ); \
+            v[SLOT] = { hash_primes( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
+                                     MZ ? step_prime( zP, kPZ, sm ) : zP, MW ? step_prime( wP, kPW, sm ) : wP ), \
+                        dxB - ( MX ? o1 : o0 ), dyB - ( MY ? o1 : o0 ), dzB - ( MZ ? o1 : o0 ), dwB - ( MW ? o1 : o0 ), sq2( fb ) }; \
         }
 
-        FN2_SS4_VERTEX( xyzwN < 0.0f, 1, 1, 1, 1, 4, fma_( o1, coordSum, stemA ) )
-        FN2_SS4_VERTEX( xyzwN < wN, 1, 1, 1, 0, 3, fma_( o1, coordSum, stemB ) - fxor( dwB, sign ) )
-        FN2_SS4_VERTEX( xyzwN < zN, 1, 1, 0, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dzB, sign ) )
-        FN2_SS4_VERTEX( xyzwN < yN, 1, 0, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dyB, sign ) )
-        FN2_SS4_VERTEX( xyzwN < xN, 0, 1, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dxB, sign ) )
-        FN2_SS4_VERTEX( xN < 0.0f, 1, 0, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dxB, sign ) )
-        FN2_SS4_VERTEX( xN < -yN, 1, 1, 0, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dyB, sign ) )
-        FN2_SS4_VERTEX( xN < -zN, 1, 0, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dzB, sign ) )
-        FN2_SS4_VERTEX( xN < -wN, 1, 0, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dwB, sign ) )
-        FN2_SS4_VERTEX( yN < 0.0f, 0, 1, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dyB, sign ) )
-        FN2_SS4_VERTEX( yN < -zN, 0, 1, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dzB, sign ) )
-        FN2_SS4_VERTEX( yN < -wN, 0, 1, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dwB, sign ) )
-        FN2_SS4_VERTEX( zN < 0.0f, 0, 0, 1, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dzB, sign ) )
-        FN2_SS4_VERTEX( zN < -wN, 0, 0, 1, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dzB + dwB, sign ) )
-        FN2_SS4_VERTEX( wN < 0.0f, 0, 0, 0, 1, 1, fma_( o0, coordSum, stemA ) + fxor( dwB, sign ) )
+        FN2_SS4_VERTEX( 1, xyzwN < 0.0f, 1, 1, 1, 1, 4, fma_( o1, coordSum, stemA ) )
+        FN2_SS4_VERTEX( 2, xyzwN < wN, 1, 1, 1, 0, 3, fma_( o1, coordSum, stemB ) - fxor( dwB, sign ) )
+        FN2_SS4_VERTEX( 3, xyzwN < zN, 1, 1, 0, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dzB, sign ) )
+        FN2_SS4_VERTEX( 4, xyzwN < yN, 1, 0, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dyB, sign ) )
+        FN2_SS4_VERTEX( 5, xyzwN < xN, 0, 1, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dxB, sign ) )
+        FN2_SS4_VERTEX( 6, xN < 0.0f, 1, 0, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dxB, sign ) )
+        FN2_SS4_VERTEX( 7, xN < -yN, 1, 1, 0, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dyB, sign ) )
+        FN2_SS4_VERTEX( 8, xN < -zN, 1, 0, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dzB, sign ) )
+        FN2_SS4_VERTEX( 9, xN < -wN, 1, 0, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dwB, sign ) )
+        FN2_SS4_VERTEX( 10, yN < 0.0f, 0, 1, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dyB, sign ) )
+        FN2_SS4_VERTEX( 11, yN < -zN, 0, 1, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dzB, sign ) )
+        FN2_SS4_VERTEX( 12, yN < -wN, 0, 1, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dwB, sign ) )
+        FN2_SS4_VERTEX( 13, zN < 0.0f, 0, 0, 1, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dzB, sign ) )
+        FN2_SS4_VERTEX( 14, zN < -wN, 0, 0, 1, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dzB + dwB, sign ) )
+        FN2_SS4_VERTEX( 15, wN < 0.0f, 0, 0, 0, 1, 1, fma_( o0, coordSum, stemA ) + fxor( dwB, sign ) )
 #undef FN2_SS4_VERTEX
+    }
+
+    FN2_DI float supersimplex4( i32 seed, float x, float y, float z, float w )
+    {
+        Verts4 v[16];
+        supersimplex4_vertices( seed, x, y, z, w, v );
+        float value = v[0].falloff * grad_dot4( v[0].hash, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
+#pragma unroll
+        for( int k = 1; k < 16; k++ ) value = fma_( v[k].falloff, grad_dot4( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].dw ), value );
         return value;
     }
 }

@@ -197,8 +197,20 @@ namespace
             }
             else
             {
-                Fail( std::string( g->GetMetadata().name ) + " is not implemented by this build yet" );
-                out << "    return 0.0f;\n";
+                // DomainWarpSimplex::Warp adds the seed offset itself, DomainWarpSuperSimplex::Warp does not
+                // [DomainWarpSimplex.inl:733,746,759 vs :1094-1128]
+                const bool super = s.nodeId == N_DomainWarpSuperSimplex;
+                const int scheme = s.i[I_K0] == 1 ? 1 : 0; // `default:` falls to OrthogonalGradientMatrix
+                // kBounding per lattice / dimension / scheme [:819-821,919-921,1073-1075,1215-1217,1435-1437,1822-1824]
+                static const float kBound[2][3][2] = {
+                    { { 70.1480577066486f, (float)( 49.918426513671875 / 2.0 ) }, { 16.281631889139874f, (float)( 32.69428253173828125 / 1.4142135623730951 ) },
+                      { 30.88161777516092f, (float)( 33.653125584827855 / 1.4142135623730951 ) } },
+                    { { 12.814453124999995f, (float)( 9.28993664146183 / 2.0 ) }, { 37.63698669623629f, (float)( 144.736422163332608 / 1.4142135623730951 ) },
+                      { 48.80058117543753f, (float)( 115.21625311930542 / 1.4142135623730951 ) } } };
+                if( !super ) out << AddSeedOffset( s );
+                out << "    return fn2::warp_simplex" << dim << "<" << ( super ? 1 : 0 ) << ", " << scheme << ">( seed, warpAmp, " << Pos( dim, "s" ) << ", " << Pos( dim );
+                for( int d = 0; d < dim; d++ ) out << ", " << Lit( kBound[super ? 1 : 0][dim - 2][scheme] * s.f[F_K0 + d] );
+                out << " );\n";
             }
             out << "}\n\n";
             return name;

@@ -47,6 +47,7 @@ GOLDEN_CASES = {
     "c4_terrain_grid3d": dict(tree=TREES["c4_terrain"], kind="grid3d", off=(0.0, 0.0, 0.0), n=(28, 24, 20), step=(6.3, 6.3, 6.3), seed=1337),
     "c5_supersimplex_pos4d": dict(tree=TREES["c5_supersimplex"], kind="pos4d", count=4099, off=(0.0, 0.0, 0.0, 0.0), seed=1337),
     "cellular_caves_grid3d": dict(tree=DEMO_TREES["cellular_caves"], kind="grid3d", off=(1.0, -2.0, 3.0), n=(20, 20, 16), step=(2.9, 2.9, 2.9), seed=-7),
+    "mountain_terrain_grid3d": dict(tree=DEMO_TREES["mountain_terrain"], kind="grid3d", off=(-40.0, 10.0, 25.0), n=(24, 20, 16), step=(9.7, 9.7, 9.7), seed=1337),
     "fbm_simplex_grid4d": dict(tree=TREES["fbm_simplex_readme"], kind="grid4d", off=(0.5, 0.25, -0.75, 9.0), n=(12, 10, 8, 6), step=(7.0, 7.0, 7.0, 7.0), seed=0x7fffffff),
 }
 

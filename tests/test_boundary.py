@@ -107,15 +107,14 @@ def test_canonical_encoding_round_trips(fn):
             assert canon == text, name
         n2 = fn.lib.fnb200CanonicalEncodedNodeTree(canon.encode(), buf, 4096)
         assert n2 == n and buf.value.decode() == canon
-        if name != "mountain_terrain":  # contains DomainWarpSimplex, which this build cannot lower yet
-            assert fn.Generator(text).kernel_source(3) == fn.Generator(canon).kernel_source(3)
+        assert fn.Generator(text).kernel_source(3) == fn.Generator(canon).kernel_source(3)
 
 
 def test_every_config_tree_lowers_and_compiles_for_sm100a(fn):
     """NVRTC needs no GPU: the generated CUDA of every config compiles to an sm_100a cubin."""
     from fastnoise2_b200 import api
     kinds = {"c2_fbm5_perlin": [api.KIND_GRID2D, api.KIND_TILEABLE2D], "c5_supersimplex": [api.KIND_POS4D, api.KIND_GRID4D]}
-    for name, text in {**fn.TREES, "cellular_caves": cases.DEMO_TREES["cellular_caves"]}.items():
+    for name, text in {**fn.TREES, **cases.DEMO_TREES}.items():
         g = fn.Generator(text)
         for kind in kinds.get(name, [api.KIND_GRID3D]):
             src = g.kernel_source(kind)
@@ -123,10 +122,10 @@ def test_every_config_tree_lowers_and_compiles_for_sm100a(fn):
             g.prepare(kind)
 
 
-def test_unsupported_node_fails_loudly(fn):
-    g = fn.Generator(cases.DEMO_TREES["mountain_terrain"])  # DomainWarpSimplex: not lowered by this build yet
+def test_incomplete_tree_fails_loudly(fn):
+    g = fn.Generator.from_metadata(13)  # FractalFBm without its required Source
     rc = fn.lib.fnb200Prepare(g.handle, 3)
-    assert rc == -4 and "DomainWarpSimplex" in fn.last_error()
+    assert rc == -4 and "source node is not set" in fn.last_error()
 
 
 def test_no_gpu_means_failure_not_fallback(fn):

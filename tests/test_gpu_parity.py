@@ -36,10 +36,11 @@ def test_golden_vectors_bit_exact(gpu):
 
 
 @pytest.mark.parametrize("name", ["c1_simplex", "c2_fbm5_perlin", "c3a_cellular_distance", "c3b_cellular_lookup_white",
-                                  "c3c_cellular_lookup_gradient", "c4_terrain", "c5_supersimplex", "fbm_simplex_readme"])
+                                  "c3c_cellular_lookup_gradient", "c4_terrain", "c5_supersimplex", "fbm_simplex_readme",
+                                  "mountain_terrain", "cellular_caves"])
 def test_config_trees_vs_strict_oracle(gpu, ref, name):
     """Seeded grids at sizes the oracle finishes in seconds; the config's own step plus a coarse one that crosses many cells."""
-    tree = gpu.TREES[name]
+    tree = {**gpu.TREES, **cases.DEMO_TREES}[name]
     shapes = {
         "c2_fbm5_perlin": [dict(kind="grid2d", off=(0.0, 0.0), n=(1024, 512), step=(0.25, 0.25)), dict(kind="grid2d", off=(-333.0, 90.5), n=(700, 300), step=(3.3, 3.3)),
                            dict(kind="tileable2d", n=(256, 192), step=(1.0, 1.0))],
@@ -101,6 +102,9 @@ def test_parameter_variants_vs_strict_oracle(gpu, ref):
     for dim_removed in range(4):
         variants.append((44, [("Remove Dimension", dim_removed)], []))
     variants.append((46, [("Rotation Type", 1)], []))
+    for warp_id in (16, 17):               # DomainWarpSimplex / SuperSimplex: both vectorization schemes, scaled axes
+        for scheme in (0, 1):
+            variants.append((warp_id, [("Vectorization Scheme", scheme), ("Seed Offset", 11)], [("Feature Scale", 31.0)]))
     variants.append((41, [("Clamp Output", 1)], []))
     variants.append((32, [("Pow", 5)], []))
     variants.append((13, [("Octaves", 7)], [("Lacunarity", 2.37)]))

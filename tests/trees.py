@@ -4,7 +4,7 @@ nodes -- so a parity test needs no encoded string for every node type."""
 
 WARP_IDS = (16, 17, 18)          # DomainWarpSimplex, DomainWarpSuperSimplex, DomainWarpGradient
 WARP_FRACTAL_IDS = (19, 20)
-UNSUPPORTED_IDS = (16, 17)       # not lowered by this build yet
+UNSUPPORTED_IDS = ()             # every node type is lowered
 
 
 class Tree:
