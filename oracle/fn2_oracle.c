@@ -2,7 +2,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use anything under oracle/.
  *
  * fn2_oracle.c: plain-C, scalar, one-point-at-a-time restatement of FastNoise2's node-graph evaluation
- * (reference: /root/reference/include/FastNoise/Generators/*.inl, Generator.inl batch drivers, and the
+ * (reference: /root/reference/include/FastNoise/Generators/ .inl files, Generator.inl batch drivers, and the
  * encoded-tree decoder of src/FastNoise/Metadata.cpp + Base64.h). Every function cites the reference lines it
  * follows. It evaluates a decoded tree recursively per point -- no SIMD lanes, no code generation -- so it shares
  * neither structure nor code with the CUDA path it checks.
@@ -12,8 +12,6 @@
  * FS::FMulAdd/FNMulAdd/FMulSub, Convert<int> = round-to-nearest-even, InvSqrt = 1/sqrt, generic (non-table)
  * gradient code paths. Pinned by tests/test_oracle.py against tests/golden/ (vectors produced by the reference's
  * own sources compiled over that shim). The reference's tests hold no expected values: PARITY UNPINNED upstream.
- *
- * Not covered (decode returns a node with supported = 0): DomainWarpSimplex / DomainWarpSuperSimplex.
  *
  * Build: gcc -O2 -std=c99 -ffp-contract=off -mfma -fPIC -shared fn2_oracle.c -o libfn2oracle.so -lm
  */
@@ -144,7 +142,7 @@ static Node* node_new( int id )
 {
     Node* n = (Node*)calloc( 1, sizeof( Node ) );
     n->id = id;
-    n->supported = id != N_DomainWarpSimplex && id != N_DomainWarpSuperSimplex;
+    n->supported = 1;
     n->scale = 100.0f; n->freq = 1.0f / 100; n->rangeMin = -1.0f; n->rangeScale = 2.0f; n->refs = 1;
     for( int k = 0; k < gSpec[id].nhybrids; k++ ) n->hval[k] = gSpec[id].hdef[k];
     switch( id ) /* member defaults of the node classes */
@@ -513,238 +511,403 @@ static float noise_perlin( i32 seed, int dim, const float* p ) /* Perlin.inl:7-1
 
 static float pow4( float v ) { v *= v; v *= v; return v; }
 
-static float noise_simplex2( i32 seed, float x, float y ) /* Simplex.inl:7-63 */
-{
-    const double R3 = 1.7320508075688772935274463415059, SK = 1.0 / ( R3 + 1.0 ), US = -1.0 / ( R3 + 3.0 );
-    float sd = (float)SK * ( x + y ), xs = x + sd, ys = y + sd, xb = floorf( xs ), yb = floorf( ys ), dxs = xs - xb, dys = ys - yb;
-    i32 P[2] = { imul( cvt_i( xb ), kPrime[0] ), imul( cvt_i( yb ), kPrime[1] ) };
-    int xge = dxs >= dys;
-    float ud = (float)US * ( dxs + dys ), dx0 = dxs + ud, dy0 = dys + ud;
-    float dx1 = ( xge ? dx0 : dx0 + 1.0f ) - (float)( US + 1 ), dy1 = ( xge ? dy0 + 1.0f : dy0 ) - (float)( US + 1 );
-    float dx2 = dx0 - (float)( US * 2 + 1 ), dy2 = dy0 - (float)( US * 2 + 1 );
-    float f0 = fnma( dx0, dx0, fnma( dy0, dy0, 0.5f ) ), f1 = fnma( dx1, dx1, fnma( dy1, dy1, 0.5f ) );
-    float f2 = f0 + fmaf( ud, (float)( -4.0 * ( R3 + 2.0 ) / ( R3 + 3.0 ) ), (float)( -2.0 / 3.0 ) );
-    f0 = pow4( fmax_x86( f0, 0.0f ) ); f1 = pow4( fmax_x86( f1, 0.0f ) ); f2 = pow4( fmax_x86( f2, 0.0f ) );
-    i32 Q1[2] = { xge ? iadd( P[0], kPrime[0] ) : P[0], xge ? P[1] : iadd( P[1], kPrime[1] ) }, Q2[2] = { iadd( P[0], kPrime[0] ), iadd( P[1], kPrime[1] ) };
-    float g0 = grad2( hash_primes( seed, P, 2 ), dx0, dy0 ), g1 = grad2( hash_primes( seed, Q1, 2 ), dx1, dy1 ), g2 = grad2( hash_primes( seed, Q2, 2 ), dx2, dy2 );
-    return fmaf( g0, f0, fmaf( g1, f1, g2 * f2 ) );
-}
+/* ---- simplex-lattice geometry. The Simplex / SuperSimplex noises and the DomainWarpSimplex / DomainWarpSuperSimplex
+ * displacement fields visit the same lattice vertices [Simplex.inl:7-936, DomainWarpSimplex.inl:771-1833]; a producer lists
+ * them in the reference's order (hash of the lattice point, offset to it, falloff^4) and each consumer folds them its way. */
+typedef struct { i32 hash; float d[4]; float falloff; } Vert;
 
-static float noise_simplex3( i32 seed, float x, float y, float z ) /* Simplex.inl:65-142 */
+static int simplex_vertices( i32 seed, int dim, const float* p, Vert* out )
 {
-    const double SK = 1.0 / 3.0, RU = -1.0 / 2.0;
-    const float R2 = (float)0.6;
-    float sd = (float)SK * ( x + y + z ), xs = x + sd, ys = y + sd, zs = z + sd;
-    float xb = floorf( xs ), yb = floorf( ys ), zb = floorf( zs ), a = xs - xb, b = ys - yb, c = zs - zb;
-    i32 P[3] = { imul( cvt_i( xb ), kPrime[0] ), imul( cvt_i( yb ), kPrime[1] ), imul( cvt_i( zb ), kPrime[2] ) };
-    int xy = a >= b, yz = b >= c, xz = a >= c;
-    float ud = (float)RU * ( a + b + c ), dx0 = a + ud, dy0 = b + ud, dz0 = c + ud;
-    int mX1 = xy && xz, mY1 = yz && !xy, mZ1 = xz || yz, nX2 = xy || xz, nY2 = xy && !yz, nZ2 = xz && yz;
-    float k3 = (float)( RU * 3 + 1 ), dx3 = dx0 - k3, dy3 = dy0 - k3, dz3 = dz0 - k3;
-    float dx1 = mX1 ? dx3 - 1.0f : dx3, dy1 = mY1 ? dy3 - 1.0f : dy3, dz1 = mZ1 ? dz3 : dz3 - 1.0f;
-    float dx2 = !nX2 ? dx0 + 1.0f : dx0, dy2 = nY2 ? dy0 + 1.0f : dy0, dz2 = nZ2 ? dz0 + 1.0f : dz0;
-    float f0 = fnma( dz0, dz0, fnma( dy0, dy0, fnma( dx0, dx0, R2 ) ) ), f1 = fnma( dz1, dz1, fnma( dy1, dy1, fnma( dx1, dx1, R2 ) ) );
-    float f2 = fnma( dz2, dz2, fnma( dy2, dy2, fnma( dx2, dx2, R2 ) ) ), f3 = f0 - ( ud + (float)( 3.0 / 4.0 ) );
-    f0 = pow4( fmax_x86( f0, 0.0f ) ); f1 = pow4( fmax_x86( f1, 0.0f ) ); f2 = pow4( fmax_x86( f2, 0.0f ) ); f3 = pow4( fmax_x86( f3, 0.0f ) );
-    i32 Q1[3] = { mX1 ? iadd( P[0], kPrime[0] ) : P[0], mY1 ? iadd( P[1], kPrime[1] ) : P[1], mZ1 ? P[2] : iadd( P[2], kPrime[2] ) };
-    i32 Q2[3] = { nX2 ? iadd( P[0], kPrime[0] ) : P[0], nY2 ? P[1] : iadd( P[1], kPrime[1] ), nZ2 ? P[2] : iadd( P[2], kPrime[2] ) };
-    i32 Q3[3] = { iadd( P[0], kPrime[0] ), iadd( P[1], kPrime[1] ), iadd( P[2], kPrime[2] ) };
-    float g0 = grad3( hash_primes( seed, P, 3 ), dx0, dy0, dz0 ), g1 = grad3( hash_primes( seed, Q1, 3 ), dx1, dy1, dz1 );
-    float g2 = grad3( hash_primes( seed, Q2, 3 ), dx2, dy2, dz2 ), g3 = grad3( hash_primes( seed, Q3, 3 ), dx3, dy3, dz3 );
-    return fmaf( g3, f3, fmaf( g2, f2, fmaf( g1, f1, g0 * f0 ) ) );
-}
-
-static float noise_simplex4( i32 seed, const float* p ) /* Simplex.inl:144-286 */
-{
-    const double R5 = 2.2360679774997896964091736687313, SK = 1.0 / ( R5 + 1.0 ), US = -1.0 / ( R5 + 5.0 );
-    const float R2 = (float)0.6;
-    float sd = (float)SK * ( p[0] + p[1] + p[2] + p[3] ), ds[4], d0[4]; i32 P[4];
-    for( int k = 0; k < 4; k++ ) { float s = p[k] + sd, b = floorf( s ); ds[k] = s - b; P[k] = imul( cvt_i( b ), kPrime[k] ); }
-    float ud = (float)US * ( ds[0] + ds[1] + ds[2] + ds[3] );
-    for( int k = 0; k < 4; k++ ) d0[k] = ds[k] + ud;
-    int rank[4] = { 0, 0, 0, 0 }; /* how many of the other coordinates each one is >= to [:180-207] */
-    for( int a = 0; a < 4; a++ ) for( int b = a + 1; b < 4; b++ ) { if( d0[a] >= d0[b] ) rank[a]++; else rank[b]++; }
-
-    float g[5], f[5], rawF0 = 0;
-    for( int v = 0; v < 5; v++ ) /* vertex v = origin plus the v highest-ranked axes */
+    if( dim == 2 ) /* Simplex.inl:7-56 */
     {
-        float d[4]; i32 Q[4];
-        for( int k = 0; k < 4; k++ )
-        {
-            int stepped = v == 4 || ( v > 0 && rank[k] > 3 - v );
-            Q[k] = stepped ? iadd( P[k], kPrime[k] ) : P[k];
-            if( v == 0 ) d[k] = d0[k];
-            else if( v == 4 ) d[k] = d0[k] - (float)( US * 4 + 1 );
-            else d[k] = ( stepped ? d0[k] - 1.0f : d0[k] ) - (float)( US * v );
-        }
-        float fall;
-        if( v == 4 ) fall = rawF0 + fmaf( ud, (float)( -4.0 * ( R5 + 3.0 ) / ( R5 + 5.0 ) ), (float)( -4.0 / 5.0 ) );
-        else fall = fnma( d[3], d[3], fnma( d[2], d[2], fnma( d[1], d[1], fnma( d[0], d[0], R2 ) ) ) );
-        if( v == 0 ) rawF0 = fall;
-        f[v] = pow4( fmax_x86( fall, 0.0f ) );
-        g[v] = grad4( hash_primes( seed, Q, 4 ), d[0], d[1], d[2], d[3] );
+        const double R3 = 1.7320508075688772935274463415059, SK = 1.0 / ( R3 + 1.0 ), US = -1.0 / ( R3 + 3.0 );
+        float x = p[0], y = p[1];
+        float sd = (float)SK * ( x + y ), xs = x + sd, ys = y + sd, xb = floorf( xs ), yb = floorf( ys ), dxs = xs - xb, dys = ys - yb;
+        i32 P[2] = { imul( cvt_i( xb ), kPrime[0] ), imul( cvt_i( yb ), kPrime[1] ) };
+        int xge = dxs >= dys;
+        float ud = (float)US * ( dxs + dys ), dx0 = dxs + ud, dy0 = dys + ud;
+        float dx1 = ( xge ? dx0 : dx0 + 1.0f ) - (float)( US + 1 ), dy1 = ( xge ? dy0 + 1.0f : dy0 ) - (float)( US + 1 );
+        float dx2 = dx0 - (float)( US * 2 + 1 ), dy2 = dy0 - (float)( US * 2 + 1 );
+        float f0 = fnma( dx0, dx0, fnma( dy0, dy0, 0.5f ) ), f1 = fnma( dx1, dx1, fnma( dy1, dy1, 0.5f ) );
+        float f2 = f0 + fmaf( ud, (float)( -4.0 * ( R3 + 2.0 ) / ( R3 + 3.0 ) ), (float)( -2.0 / 3.0 ) );
+        i32 Q1[2] = { xge ? iadd( P[0], kPrime[0] ) : P[0], xge ? P[1] : iadd( P[1], kPrime[1] ) }, Q2[2] = { iadd( P[0], kPrime[0] ), iadd( P[1], kPrime[1] ) };
+        out[0].hash = hash_primes( seed, P, 2 ); out[0].d[0] = dx0; out[0].d[1] = dy0; out[0].falloff = pow4( fmax_x86( f0, 0.0f ) );
+        out[1].hash = hash_primes( seed, Q1, 2 ); out[1].d[0] = dx1; out[1].d[1] = dy1; out[1].falloff = pow4( fmax_x86( f1, 0.0f ) );
+        out[2].hash = hash_primes( seed, Q2, 2 ); out[2].d[0] = dx2; out[2].d[1] = dy2; out[2].falloff = pow4( fmax_x86( f2, 0.0f ) );
+        return 3;
     }
-    return fmaf( g[0], f[0], fmaf( g[1], f[1], fmaf( g[2], f[2], fmaf( g[3], f[3], g[4] * f[4] ) ) ) );
+    if( dim == 3 ) /* Simplex.inl:65-135 */
+    {
+        const double SK = 1.0 / 3.0, RU = -1.0 / 2.0;
+        const float R2 = (float)0.6;
+        float x = p[0], y = p[1], z = p[2];
+        float sd = (float)SK * ( x + y + z ), xs = x + sd, ys = y + sd, zs = z + sd;
+        float xb = floorf( xs ), yb = floorf( ys ), zb = floorf( zs ), a = xs - xb, b = ys - yb, c = zs - zb;
+        i32 P[3] = { imul( cvt_i( xb ), kPrime[0] ), imul( cvt_i( yb ), kPrime[1] ), imul( cvt_i( zb ), kPrime[2] ) };
+        int xy = a >= b, yz = b >= c, xz = a >= c;
+        float ud = (float)RU * ( a + b + c ), dx0 = a + ud, dy0 = b + ud, dz0 = c + ud;
+        int mX1 = xy && xz, mY1 = yz && !xy, mZ1 = xz || yz, nX2 = xy || xz, nY2 = xy && !yz, nZ2 = xz && yz;
+        float k3 = (float)( RU * 3 + 1 ), dx3 = dx0 - k3, dy3 = dy0 - k3, dz3 = dz0 - k3;
+        float dx1 = mX1 ? dx3 - 1.0f : dx3, dy1 = mY1 ? dy3 - 1.0f : dy3, dz1 = mZ1 ? dz3 : dz3 - 1.0f;
+        float dx2 = !nX2 ? dx0 + 1.0f : dx0, dy2 = nY2 ? dy0 + 1.0f : dy0, dz2 = nZ2 ? dz0 + 1.0f : dz0;
+        float f0 = fnma( dz0, dz0, fnma( dy0, dy0, fnma( dx0, dx0, R2 ) ) ), f1 = fnma( dz1, dz1, fnma( dy1, dy1, fnma( dx1, dx1, R2 ) ) );
+        float f2 = fnma( dz2, dz2, fnma( dy2, dy2, fnma( dx2, dx2, R2 ) ) ), f3 = f0 - ( ud + (float)( 3.0 / 4.0 ) );
+        i32 Q1[3] = { mX1 ? iadd( P[0], kPrime[0] ) : P[0], mY1 ? iadd( P[1], kPrime[1] ) : P[1], mZ1 ? P[2] : iadd( P[2], kPrime[2] ) };
+        i32 Q2[3] = { nX2 ? iadd( P[0], kPrime[0] ) : P[0], nY2 ? P[1] : iadd( P[1], kPrime[1] ), nZ2 ? P[2] : iadd( P[2], kPrime[2] ) };
+        i32 Q3[3] = { iadd( P[0], kPrime[0] ), iadd( P[1], kPrime[1] ), iadd( P[2], kPrime[2] ) };
+        const i32* Q[4] = { P, Q1, Q2, Q3 };
+        float dd[4][3] = { { dx0, dy0, dz0 }, { dx1, dy1, dz1 }, { dx2, dy2, dz2 }, { dx3, dy3, dz3 } }, ff[4] = { f0, f1, f2, f3 };
+        for( int v = 0; v < 4; v++ )
+        {
+            out[v].hash = hash_primes( seed, Q[v], 3 );
+            for( int k = 0; k < 3; k++ ) out[v].d[k] = dd[v][k];
+            out[v].falloff = pow4( fmax_x86( ff[v], 0.0f ) );
+        }
+        return 4;
+    }
+    { /* Simplex.inl:144-279 */
+        const double R5 = 2.2360679774997896964091736687313, SK = 1.0 / ( R5 + 1.0 ), US = -1.0 / ( R5 + 5.0 );
+        const float R2 = (float)0.6;
+        float sd = (float)SK * ( p[0] + p[1] + p[2] + p[3] ), ds[4], d0[4]; i32 P[4];
+        for( int k = 0; k < 4; k++ ) { float s = p[k] + sd, b = floorf( s ); ds[k] = s - b; P[k] = imul( cvt_i( b ), kPrime[k] ); }
+        float ud = (float)US * ( ds[0] + ds[1] + ds[2] + ds[3] );
+        for( int k = 0; k < 4; k++ ) d0[k] = ds[k] + ud;
+        int rank[4] = { 0, 0, 0, 0 }; /* how many of the other coordinates each one is >= to [:180-207] */
+        for( int a = 0; a < 4; a++ ) for( int b = a + 1; b < 4; b++ ) { if( d0[a] >= d0[b] ) rank[a]++; else rank[b]++; }
+        float rawF0 = 0;
+        for( int v = 0; v < 5; v++ ) /* vertex v = origin plus the v highest-ranked axes */
+        {
+            float* d = out[v].d; i32 Q[4];
+            for( int k = 0; k < 4; k++ )
+            {
+                int stepped = v == 4 || ( v > 0 && rank[k] > 3 - v );
+                Q[k] = stepped ? iadd( P[k], kPrime[k] ) : P[k];
+                if( v == 0 ) d[k] = d0[k];
+                else if( v == 4 ) d[k] = d0[k] - (float)( US * 4 + 1 );
+                else d[k] = ( stepped ? d0[k] - 1.0f : d0[k] ) - (float)( US * v );
+            }
+            float fall;
+            if( v == 4 ) fall = rawF0 + fmaf( ud, (float)( -4.0 * ( R5 + 3.0 ) / ( R5 + 5.0 ) ), (float)( -4.0 / 5.0 ) );
+            else fall = fnma( d[3], d[3], fnma( d[2], d[2], fnma( d[1], d[1], fnma( d[0], d[0], R2 ) ) ) );
+            if( v == 0 ) rawF0 = fall;
+            out[v].falloff = pow4( fmax_x86( fall, 0.0f ) );
+            out[v].hash = hash_primes( seed, Q, 4 );
+        }
+        return 5;
+    }
+}
+
+static float noise_simplex( i32 seed, int dim, const float* p )
+{
+    Vert v[5];
+    int n = simplex_vertices( seed, dim, p, v );
+    float g[5];
+    for( int k = 0; k < n; k++ ) g[k] = grad_n( dim, v[k].hash, v[k].d );
+    if( dim == 3 ) /* fma( g3, f3, fma( g2, f2, fma( g1, f1, g0 * f0 ) ) ) [Simplex.inl:137] */
+    {
+        float value = g[0] * v[0].falloff;
+        for( int k = 1; k < n; k++ ) value = fmaf( g[k], v[k].falloff, value );
+        return value;
+    }
+    /* 2D and 4D fold from the last vertex inwards [Simplex.inl:58, 281] */
+    float value = g[n - 1] * v[n - 1].falloff;
+    for( int k = n - 2; k >= 0; k-- ) value = fmaf( g[k], v[k].falloff, value );
+    return value;
 }
 
 /* ---- SuperSimplex [Simplex.inl:293-936] */
 static float sq2( float v ) { return ( v * v ) * ( v * v ); }
 
-static float noise_supersimplex2( i32 seed, float x, float y ) /* :293-377 */
-{
-    const double R3 = 1.7320508075688772935274463415059, SK = 1.0 / ( R3 + 1.0 ), US = -1.0 / ( R3 + 3.0 );
-    const float R2 = (float)( 2.0 / 3.0 );
-    float sd = (float)SK * ( x + y ), xs = x + sd, ys = y + sd, xb = floorf( xs ), yb = floorf( ys ), dxs = xs - xb, dys = ys - yb;
-    i32 X = imul( cvt_i( xb ), kPrime[0] ), Y = imul( cvt_i( yb ), kPrime[1] );
-    int fwdXY = dxs + dys > 1.0f;
-    float bound = fwdXY ? -1.0f : 0.0f;
-    int fwdX = fmaf( dxs, -2.0f, dys ) < bound, fwdY = fmaf( dys, -2.0f, dxs ) < bound;
-    float ud = (float)US * ( dxs + dys ), dx = dxs + ud, dy = dys + ud;
-    i32 Q[2] = { X, Y };
-    float base0 = fnma( dx, dx, fnma( dy, dy, R2 ) );
-    float value = pow4( base0 ) * grad2( hash_primes( seed, Q, 2 ), dx, dy );
-    Q[0] = iadd( X, kPrime[0] ); Q[1] = iadd( Y, kPrime[1] );
-    {
-        float g = grad2( hash_primes( seed, Q, 2 ), dx - (float)( 2 * US + 1 ), dy - (float)( 2 * US + 1 ) );
-        float fall = fmaf( ud, (float)( -4.0 * ( R3 + 2.0 ) / ( R3 + 3.0 ) ), base0 - R2 );
-        value = fmaf( pow4( fall ), g, value );
-    }
-    float delta = fwdXY ? (float)( US + 1 ) : (float)( -US );
-    dx -= delta; dy -= delta;
-    {
-        i32 qx = fwdX ? iadd( X, imul( kPrime[0], 2 ) ) : X;
-        Q[0] = fwdXY ? qx : isub( qx, kPrime[0] ); Q[1] = fwdXY ? iadd( Y, kPrime[1] ) : Y;
-        float ex = dx - ( fwdX ? (float)( 1 + 2 * US ) : -1.0f ), ey = fwdX ? dy - (float)( 2 * US ) : dy;
-        float fall = fmax_x86( fnma( ex, ex, fnma( ey, ey, R2 ) ), 0.0f );
-        value = fmaf( pow4( fall ), grad2( hash_primes( seed, Q, 2 ), ex, ey ), value );
-    }
-    {
-        i32 qy = fwdY ? iadd( Y, imul( kPrime[1], 2 ) ) : Y;
-        Q[0] = fwdXY ? iadd( X, kPrime[0] ) : X; Q[1] = fwdXY ? qy : isub( qy, kPrime[1] );
-        float ex = fwdY ? dx - (float)( 2 * US ) : dx, ey = dy - ( fwdY ? (float)( 1 + 2 * US ) : -1.0f );
-        float fall = fmax_x86( fnma( ex, ex, fnma( ey, ey, R2 ) ), 0.0f );
-        value = fmaf( pow4( fall ), grad2( hash_primes( seed, Q, 2 ), ex, ey ), value );
-    }
-    return value;
-}
-
 /* closest-vertex search shared by 3D and 4D: a running best score and the axis mask of its vertex */
 typedef struct { float best; i32 bits; } Closest;
 static void consider( Closest* c, float score, i32 bits ) { if( score > c->best ) c->bits = bits; c->best = fmax_x86( c->best, score ); }
 
-static float noise_supersimplex3( i32 seed, float x, float y, float z ) /* :379-576 */
+static int supersimplex_vertices( i32 seed, int dim, const float* p, Vert* out )
 {
-    const double SK = 1.0 / 3.0, RU = -1.0 / 2.0, TU = -1.0 / 4.0, A = 3.0 / 4.0, B = 1.0;
-    float sd = (float)SK * ( x + y + z ), s[3] = { x + sd, y + sd, z + sd }, base[3], d[3];
-    for( int k = 0; k < 3; k++ ) { base[k] = floorf( s[k] ); d[k] = s[k] - base[k]; }
+    if( dim == 2 ) /* :293-372 */
     {
-        float tud = (float)TU * ( d[0] + d[1] + d[2] ), nx = d[0] + tud, ny = d[1] + tud, nz = d[2] + tud, nn = -tud;
-        Closest c = { 0.375f, 0 };
-        c.bits = nn > c.best ? -1 : 0; c.best = fmax_x86( c.best, nn );
-        consider( &c, nx, 1 ); consider( &c, ny, 2 ); consider( &c, nz, 4 );
-        c.best += 0.125f - nn;
-        consider( &c, -nz, 3 ); consider( &c, -ny, 5 ); consider( &c, -nx, 6 );
-        for( int k = 0; k < 3; k++ ) if( c.bits & ( 1 << k ) ) { base[k] = base[k] + 1.0f; d[k] = d[k] - 1.0f; }
+        const double R3 = 1.7320508075688772935274463415059, SK = 1.0 / ( R3 + 1.0 ), US = -1.0 / ( R3 + 3.0 );
+        const float R2 = (float)( 2.0 / 3.0 );
+        float x = p[0], y = p[1];
+        float sd = (float)SK * ( x + y ), xs = x + sd, ys = y + sd, xb = floorf( xs ), yb = floorf( ys ), dxs = xs - xb, dys = ys - yb;
+        i32 X = imul( cvt_i( xb ), kPrime[0] ), Y = imul( cvt_i( yb ), kPrime[1] );
+        int fwdXY = dxs + dys > 1.0f;
+        float bound = fwdXY ? -1.0f : 0.0f;
+        int fwdX = fmaf( dxs, -2.0f, dys ) < bound, fwdY = fmaf( dys, -2.0f, dxs ) < bound;
+        float ud = (float)US * ( dxs + dys ), dx = dxs + ud, dy = dys + ud;
+        i32 Q[2] = { X, Y };
+        float base0 = fnma( dx, dx, fnma( dy, dy, R2 ) );
+        out[0].hash = hash_primes( seed, Q, 2 ); out[0].d[0] = dx; out[0].d[1] = dy; out[0].falloff = pow4( base0 );
+        Q[0] = iadd( X, kPrime[0] ); Q[1] = iadd( Y, kPrime[1] );
+        out[1].hash = hash_primes( seed, Q, 2 ); out[1].d[0] = dx - (float)( 2 * US + 1 ); out[1].d[1] = dy - (float)( 2 * US + 1 );
+        out[1].falloff = pow4( fmaf( ud, (float)( -4.0 * ( R3 + 2.0 ) / ( R3 + 3.0 ) ), base0 - R2 ) );
+        float delta = fwdXY ? (float)( US + 1 ) : (float)( -US );
+        dx -= delta; dy -= delta;
+        {
+            i32 qx = fwdX ? iadd( X, imul( kPrime[0], 2 ) ) : X;
+            Q[0] = fwdXY ? qx : isub( qx, kPrime[0] ); Q[1] = fwdXY ? iadd( Y, kPrime[1] ) : Y;
+            float ex = dx - ( fwdX ? (float)( 1 + 2 * US ) : -1.0f ), ey = fwdX ? dy - (float)( 2 * US ) : dy;
+            out[2].hash = hash_primes( seed, Q, 2 ); out[2].d[0] = ex; out[2].d[1] = ey;
+            out[2].falloff = pow4( fmax_x86( fnma( ex, ex, fnma( ey, ey, R2 ) ), 0.0f ) );
+        }
+        {
+            i32 qy = fwdY ? iadd( Y, imul( kPrime[1], 2 ) ) : Y;
+            Q[0] = fwdXY ? iadd( X, kPrime[0] ) : X; Q[1] = fwdXY ? qy : isub( qy, kPrime[1] );
+            float ex = fwdY ? dx - (float)( 2 * US ) : dx, ey = dy - ( fwdY ? (float)( 1 + 2 * US ) : -1.0f );
+            out[3].hash = hash_primes( seed, Q, 2 ); out[3].d[0] = ex; out[3].d[1] = ey;
+            out[3].falloff = pow4( fmax_x86( fnma( ex, ex, fnma( ey, ey, R2 ) ), 0.0f ) );
+        }
+        return 4;
     }
-    i32 P[3];
-    for( int k = 0; k < 3; k++ ) P[k] = imul( cvt_i( base[k] ), kPrime[k] );
-    float sum = d[0] + d[1] + d[2], tud = (float)TU * sum, N[3] = { d[0] + tud, d[1] + tud, d[2] + tud }, nn = -tud;
-    float ud = (float)RU * sum, D[3] = { d[0] + ud, d[1] + ud, d[2] + ud };
-    float coordSum = (float)( 1 + 3 * RU ) * sum;
-
-    float fb = fnma( D[2], D[2], fnma( D[1], D[1], fnma( D[0], D[0], (float)A ) ) ) * 0.5f;
-    float stemA = fb - (float)( A * 0.5 ), stemB = fb - (float)( B * 0.5 );
-    float value = sq2( fb ) * grad3( hash_primes( seed, P, 3 ), D[0], D[1], D[2] );
-
-    /* the 7 neighbours, in the reference's order: mask of stepping axes */
-    static const int kMask[7] = { 7, 3, 5, 6, 1, 2, 4 };
-    for( int v = 0; v < 7; v++ )
+    if( dim == 3 ) /* :379-572 */
     {
-        int mask = kMask[v], axes = ( mask & 1 ) + ( ( mask >> 1 ) & 1 ) + ( ( mask >> 2 ) & 1 );
-        int neg;
-        if( axes == 3 ) neg = nn < 0.0f;
-        else if( axes == 2 ) neg = nn < N[mask == 3 ? 2 : ( mask == 5 ? 1 : 0 )]; /* compared with the axis that does NOT step */
-        else neg = N[mask == 1 ? 0 : ( mask == 2 ? 1 : 2 )] < 0.0f;
-        i32 sign = neg ? (i32)0x80000000u : 0, Q[3];
-        for( int k = 0; k < 3; k++ ) Q[k] = ( mask >> k ) & 1 ? iadd( P[k], neg ? isub( 0, kPrime[k] ) : kPrime[k] ) : P[k];
-        float e[3], fall;
-        if( axes == 3 )
+        const double SK = 1.0 / 3.0, RU = -1.0 / 2.0, TU = -1.0 / 4.0, A = 3.0 / 4.0, B = 1.0;
+        float x = p[0], y = p[1], z = p[2];
+        float sd = (float)SK * ( x + y + z ), s[3] = { x + sd, y + sd, z + sd }, base[3], d[3];
+        for( int k = 0; k < 3; k++ ) { base[k] = floorf( s[k] ); d[k] = s[k] - base[k]; }
         {
-            float o = fxor( (float)( 3 * RU + 1 ), sign );
-            for( int k = 0; k < 3; k++ ) e[k] = D[k] - o;
-            fall = fmax_x86( fmaf( o, coordSum, stemA ), 0.0f );
+            float tud = (float)TU * ( d[0] + d[1] + d[2] ), nx = d[0] + tud, ny = d[1] + tud, nz = d[2] + tud, nn = -tud;
+            Closest c = { 0.375f, 0 };
+            c.bits = nn > c.best ? -1 : 0; c.best = fmax_x86( c.best, nn );
+            consider( &c, nx, 1 ); consider( &c, ny, 2 ); consider( &c, nz, 4 );
+            c.best += 0.125f - nn;
+            consider( &c, -nz, 3 ); consider( &c, -ny, 5 ); consider( &c, -nx, 6 );
+            for( int k = 0; k < 3; k++ ) if( c.bits & ( 1 << k ) ) { base[k] = base[k] + 1.0f; d[k] = d[k] - 1.0f; }
         }
-        else if( axes == 2 )
+        i32 P[3];
+        for( int k = 0; k < 3; k++ ) P[k] = imul( cvt_i( base[k] ), kPrime[k] );
+        float sum = d[0] + d[1] + d[2], tud = (float)TU * sum, N[3] = { d[0] + tud, d[1] + tud, d[2] + tud }, nn = -tud;
+        float ud = (float)RU * sum, D[3] = { d[0] + ud, d[1] + ud, d[2] + ud };
+        float coordSum = (float)( 1 + 3 * RU ) * sum;
+
+        float fb = fnma( D[2], D[2], fnma( D[1], D[1], fnma( D[0], D[0], (float)A ) ) ) * 0.5f;
+        float stemA = fb - (float)( A * 0.5 ), stemB = fb - (float)( B * 0.5 );
+        out[0].hash = hash_primes( seed, P, 3 ); out[0].falloff = sq2( fb );
+        for( int k = 0; k < 3; k++ ) out[0].d[k] = D[k];
+
+        /* the 7 neighbours, in the reference's order: mask of stepping axes */
+        static const int kMask[7] = { 7, 3, 5, 6, 1, 2, 4 };
+        for( int v = 0; v < 7; v++ )
         {
-            int still = mask == 3 ? 2 : ( mask == 5 ? 1 : 0 );
-            float o0 = fxor( (float)( 2 * RU ), sign );
-            for( int k = 0; k < 3; k++ ) e[k] = k == still ? D[k] - o0 : D[k];
-            fall = fmin_x86( fxor( D[still], sign ) - stemB, 0.0f );
+            int mask = kMask[v], axes = ( mask & 1 ) + ( ( mask >> 1 ) & 1 ) + ( ( mask >> 2 ) & 1 );
+            int neg;
+            if( axes == 3 ) neg = nn < 0.0f;
+            else if( axes == 2 ) neg = nn < N[mask == 3 ? 2 : ( mask == 5 ? 1 : 0 )]; /* compared with the axis that does NOT step */
+            else neg = N[mask == 1 ? 0 : ( mask == 2 ? 1 : 2 )] < 0.0f;
+            i32 sign = neg ? (i32)0x80000000u : 0, Q[3];
+            for( int k = 0; k < 3; k++ ) Q[k] = ( mask >> k ) & 1 ? iadd( P[k], neg ? isub( 0, kPrime[k] ) : kPrime[k] ) : P[k];
+            float* e = out[v + 1].d; float fall;
+            if( axes == 3 )
+            {
+                float o = fxor( (float)( 3 * RU + 1 ), sign );
+                for( int k = 0; k < 3; k++ ) e[k] = D[k] - o;
+                fall = fmax_x86( fmaf( o, coordSum, stemA ), 0.0f );
+            }
+            else if( axes == 2 )
+            {
+                int still = mask == 3 ? 2 : ( mask == 5 ? 1 : 0 );
+                float o0 = fxor( (float)( 2 * RU ), sign );
+                for( int k = 0; k < 3; k++ ) e[k] = k == still ? D[k] - o0 : D[k];
+                fall = fmin_x86( fxor( D[still], sign ) - stemB, 0.0f );
+            }
+            else
+            {
+                int moving = mask == 1 ? 0 : ( mask == 2 ? 1 : 2 );
+                float o0 = fxor( (float)RU, sign );
+                for( int k = 0; k < 3; k++ ) e[k] = k == moving ? D[k] + o0 : D[k] - o0;
+                fall = fmax_x86( fmaf( o0, coordSum, stemA ) + fxor( D[moving], sign ), 0.0f );
+            }
+            out[v + 1].hash = hash_primes( seed, Q, 3 );
+            out[v + 1].falloff = sq2( fall );
         }
-        else
-        {
-            int moving = mask == 1 ? 0 : ( mask == 2 ? 1 : 2 );
-            float o0 = fxor( (float)RU, sign );
-            for( int k = 0; k < 3; k++ ) e[k] = k == moving ? D[k] + o0 : D[k] - o0;
-            fall = fmax_x86( fmaf( o0, coordSum, stemA ) + fxor( D[moving], sign ), 0.0f );
-        }
-        value = fmaf( sq2( fall ), grad3( hash_primes( seed, Q, 3 ), e[0], e[1], e[2] ), value );
+        return 8;
     }
+    { /* :578-931 */
+        const double R5 = 2.2360679774997896964091736687313, SK = 1.0 / ( R5 + 1.0 ), US = -1.0 / ( R5 + 5.0 ), TU = -1.0 / 5.0, A = 4.0 / 5.0, B = 6.0 / 5.0;
+        float sd = (float)SK * ( p[0] + p[1] + p[2] + p[3] ), base[4], d[4];
+        for( int k = 0; k < 4; k++ ) { float s = p[k] + sd; base[k] = floorf( s ); d[k] = s - base[k]; }
+        {
+            float tud = (float)TU * ( d[0] + d[1] + d[2] + d[3] ), nx = d[0] + tud, ny = d[1] + tud, nz = d[2] + tud, nw = d[3] + tud, nn = -tud;
+            Closest c; c.best = 0.6f - nn; c.bits = 0.2f > c.best ? -1 : 0; c.best = fmax_x86( c.best, 0.2f );
+            consider( &c, -nw, 7 ); consider( &c, -nz, 11 ); consider( &c, -ny, 13 ); consider( &c, -nx, 14 );
+            c.best += nn - 0.2f;
+            consider( &c, nx, 1 ); consider( &c, ny, 2 ); consider( &c, nz, 4 ); consider( &c, nw, 8 );
+            c.best += 0.2f - nx;
+            consider( &c, ny, 3 ); consider( &c, nz, 5 ); consider( &c, nw, 9 );
+            c.best += nx;
+            consider( &c, ny + nz, 6 );
+            c.best -= nw;
+            consider( &c, ny, 10 ); consider( &c, nz, 12 );
+            for( int k = 0; k < 4; k++ ) if( c.bits & ( 1 << k ) ) { base[k] = base[k] + 1.0f; d[k] = d[k] - 1.0f; }
+        }
+        i32 P[4];
+        for( int k = 0; k < 4; k++ ) P[k] = imul( cvt_i( base[k] ), kPrime[k] );
+        float sum = d[0] + d[1] + d[2] + d[3], tud = (float)TU * sum, N[4], D[4], nn = -tud, ud = (float)US * sum;
+        for( int k = 0; k < 4; k++ ) { N[k] = d[k] + tud; D[k] = d[k] + ud; }
+        float coordSum = (float)( 1 + 4 * US ) * sum;
+
+        float fb = fnma( D[3], D[3], fnma( D[2], D[2], fnma( D[1], D[1], fnma( D[0], D[0], (float)A ) ) ) ) * 0.5f;
+        float stemA = fb - (float)( A * 0.5 ), stemB = fb - (float)( B * 0.5 );
+        out[0].hash = hash_primes( seed, P, 4 ); out[0].falloff = sq2( fb );
+        for( int k = 0; k < 4; k++ ) out[0].d[k] = D[k];
+
+        /* the 15 neighbours in the reference's accumulation order, as masks of stepping axes (bit k = axis k) */
+        static const int kMask[15] = { 15, 7, 11, 13, 14, 1, 3, 5, 9, 2, 6, 10, 4, 12, 8 };
+        for( int v = 0; v < 15; v++ )
+        {
+            int mask = kMask[v], axes = 0, lo = -1, hi = -1, still = -1;
+            for( int k = 0; k < 4; k++ ) { if( ( mask >> k ) & 1 ) { axes++; if( lo < 0 ) lo = k; hi = k; } else still = k; }
+            int neg;
+            if( axes == 4 ) neg = nn < 0.0f;
+            else if( axes == 3 ) neg = nn < N[still];
+            else if( axes == 2 ) neg = N[lo] < -N[hi];
+            else neg = N[lo] < 0.0f;
+            i32 sign = neg ? (i32)0x80000000u : 0, Q[4];
+            for( int k = 0; k < 4; k++ ) Q[k] = ( mask >> k ) & 1 ? iadd( P[k], neg ? isub( 0, kPrime[k] ) : kPrime[k] ) : P[k];
+            float o1 = fxor( (float)( axes * US + 1 ), sign ), o0 = fxor( (float)( axes * US ), sign ), fall;
+            float* e = out[v + 1].d;
+            for( int k = 0; k < 4; k++ ) e[k] = D[k] - ( ( mask >> k ) & 1 ? o1 : o0 );
+            if( axes == 4 ) fall = fmaf( o1, coordSum, stemA );
+            else if( axes == 3 ) fall = fmaf( o1, coordSum, stemB ) - fxor( D[still], sign );
+            else if( axes == 2 ) fall = fmaf( o0, coordSum, stemB ) + fxor( D[lo] + D[hi], sign );
+            else fall = fmaf( o0, coordSum, stemA ) + fxor( D[lo], sign );
+            out[v + 1].hash = hash_primes( seed, Q, 4 );
+            out[v + 1].falloff = sq2( fmax_x86( fall, 0.0f ) );
+        }
+        return 16;
+    }
+}
+
+static float noise_supersimplex( i32 seed, int dim, const float* p )
+{
+    Vert v[16];
+    int n = supersimplex_vertices( seed, dim, p, v );
+    float value = v[0].falloff * grad_n( dim, v[0].hash, v[0].d );
+    for( int k = 1; k < n; k++ ) value = fmaf( v[k].falloff, grad_n( dim, v[k].hash, v[k].d ), value );
     return value;
 }
 
-static float noise_supersimplex4( i32 seed, const float* p ) /* :578-936 */
+/* ---- vector contributions of the simplex warps, generic code paths [DomainWarpSimplex.inl:7-686] */
+static float sel_hi( i32 selector, float a, float b ) { return selector < 0 ? a : b; }
+#define SKEW2F ( (float)( 1.0 / ( 1.7320508075688772935274463415059 + 1.0 ) ) )
+#define SKEW4F ( (float)( 1.0 / ( 2.2360679774997896964091736687313 + 1.0 ) ) )
+#define ROOT2F ( (float)1.4142135623730950488016887242097 )
+#define ROOT3F ( (float)1.7320508075688772935274463415059 )
+
+static void gop4_direction( i32 index, float* g ) /* :149-166 */
 {
-    const double R5 = 2.2360679774997896964091736687313, SK = 1.0 / ( R5 + 1.0 ), US = -1.0 / ( R5 + 5.0 ), TU = -1.0 / 5.0, A = 4.0 / 5.0, B = 6.0 / 5.0;
-    float sd = (float)SK * ( p[0] + p[1] + p[2] + p[3] ), base[4], d[4];
-    for( int k = 0; k < 4; k++ ) { float s = p[k] + sd; base[k] = floorf( s ); d[k] = s - base[k]; }
+    i32 a = index & ( 0x03 << 27 ), b = ( asr( index, 2 ) & ( 0x07 << 27 ) ) ^ a;
+    int extra = b >= ( 0x04 << 27 ), equal = a == b;
+    if( equal ) a = -1;
+    float neutral = ( equal || extra ) ? ( extra ? SKEW4F * -1.0f : SKEW4F ) : 0.0f;
+    for( int k = 0; k < 4; k++ )
     {
-        float tud = (float)TU * ( d[0] + d[1] + d[2] + d[3] ), nx = d[0] + tud, ny = d[1] + tud, nz = d[2] + tud, nw = d[3] + tud, nn = -tud;
-        Closest c; c.best = 0.6f - nn; c.bits = 0.2f > c.best ? -1 : 0; c.best = fmax_x86( c.best, 0.2f );
-        consider( &c, -nw, 7 ); consider( &c, -nz, 11 ); consider( &c, -ny, 13 ); consider( &c, -nx, 14 );
-        c.best += nn - 0.2f;
-        consider( &c, nx, 1 ); consider( &c, ny, 2 ); consider( &c, nz, 4 ); consider( &c, nw, 8 );
-        c.best += 0.2f - nx;
-        consider( &c, ny, 3 ); consider( &c, nz, 5 ); consider( &c, nw, 9 );
-        c.best += nx;
-        consider( &c, ny + nz, 6 );
-        c.best -= nw;
-        consider( &c, ny, 10 ); consider( &c, nz, 12 );
-        for( int k = 0; k < 4; k++ ) if( c.bits & ( 1 << k ) ) { base[k] = base[k] + 1.0f; d[k] = d[k] - 1.0f; }
+        float t = a == shl( k, 27 ) ? neutral - 1.0f : neutral;
+        g[k] = b == shl( k, 27 ) ? t + 1.0f : t;
     }
-    i32 P[4];
-    for( int k = 0; k < 4; k++ ) P[k] = imul( cvt_i( base[k] ), kPrime[k] );
-    float sum = d[0] + d[1] + d[2] + d[3], tud = (float)TU * sum, N[4], D[4], nn = -tud, ud = (float)US * sum;
-    for( int k = 0; k < 4; k++ ) { N[k] = d[k] + tud; D[k] = d[k] + ud; }
-    float coordSum = (float)( 1 + 4 * US ) * sum;
+}
 
-    float fb = fnma( D[3], D[3], fnma( D[2], D[2], fnma( D[1], D[1], fnma( D[0], D[0], (float)A ) ) ) ) * 0.5f;
-    float stemA = fb - (float)( A * 0.5 ), stemB = fb - (float)( B * 0.5 );
-    float value = sq2( fb ) * grad4( hash_primes( seed, P, 4 ), D[0], D[1], D[2], D[3] );
-
-    /* the 15 neighbours in the reference's accumulation order, as masks of stepping axes (bit k = axis k) */
-    static const int kMask[15] = { 15, 7, 11, 13, 14, 1, 3, 5, 9, 2, 6, 10, 4, 12, 8 };
-    for( int v = 0; v < 15; v++ )
+static void vec_contribution( int scheme, int dim, i32 hash, const float* f, float m, float* value )
+{
+    if( scheme == 1 && dim == 2 ) /* GradientOuterProduct 2D :7-60 */
     {
-        int mask = kMask[v], axes = 0, lo = -1, hi = -1, still = -1;
-        for( int k = 0; k < 4; k++ ) { if( ( mask >> k ) & 1 ) { axes++; if( lo < 0 ) lo = k; hi = k; } else still = k; }
-        int neg;
-        if( axes == 4 ) neg = nn < 0.0f;
-        else if( axes == 3 ) neg = nn < N[still];
-        else if( axes == 2 ) neg = N[lo] < -N[hi];
-        else neg = N[lo] < 0.0f;
-        i32 sign = neg ? (i32)0x80000000u : 0, Q[4];
-        for( int k = 0; k < 4; k++ ) Q[k] = ( mask >> k ) & 1 ? iadd( P[k], neg ? isub( 0, kPrime[k] ) : kPrime[k] ) : P[k];
-        float o1 = fxor( (float)( axes * US + 1 ), sign ), o0 = fxor( (float)( axes * US ), sign ), e[4], fall;
-        for( int k = 0; k < 4; k++ ) e[k] = D[k] - ( ( mask >> k ) & 1 ? o1 : o0 );
-        if( axes == 4 ) fall = fmaf( o1, coordSum, stemA );
-        else if( axes == 3 ) fall = fmaf( o1, coordSum, stemB ) - fxor( D[still], sign );
-        else if( axes == 2 ) fall = fmaf( o0, coordSum, stemB ) + fxor( D[lo] + D[hi], sign );
-        else fall = fmaf( o0, coordSum, stemA ) + fxor( D[lo], sign );
-        fall = fmax_x86( fall, 0.0f );
-        value = fmaf( sq2( fall ), grad4( hash_primes( seed, Q, 4 ), e[0], e[1], e[2], e[3] ), value );
+        i32 hs = lsr( hash, 1 ), ig = imul( hs, 3 ), io = imul( hs, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
+        float u = sel_hi( shl( ig, 2 ), f[1], f[0] ), v = sel_hi( shl( ig, 2 ), f[0], f[1] );
+        float a = u * sel_hi( ig, 2.0f, ROOT3F ), b = fxor( v, shl( asr( ig, 30 ), 31 ) );
+        m *= fxor( ig >= 0 ? a + b : a, shl( asr( ig, 28 ) ^ io, 31 ) );
+        a = m * sel_hi( io, 2.0f, ROOT3F );
+        b = fxor( io >= 0 ? m : 0.0f, shl( asr( io, 30 ), 31 ) );
+        value[0] += sel_hi( shl( io, 30 ), b, a );
+        value[1] += sel_hi( shl( io, 30 ), a, b );
     }
-    return value;
+    else if( scheme == 1 && dim == 3 ) /* :62-119 */
+    {
+        i32 hs = lsr( hash, 1 ), ig = lsr( imul( hs, 3 ), 28 ), io = imul( hs, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
+        io |= asr( io, 28 );
+        float u = ig >= 8 ? f[1] : f[0], v = ig >= 4 ? f[2] : f[1];
+        m *= fxor( u, shl( ig, 31 ) ) + fxor( v, shl( asr( ig, 1 ), 31 ) );
+        io &= 0xF;
+        float s0 = fxor( m, shl( io, 31 ) ), s1 = fxor( m, shl( asr( io, 1 ), 31 ) );
+        int notYZ = io < 8, notXY = io >= 4;
+        if( notYZ ) value[0] = value[0] + s0;
+        if( notXY ) value[2] = value[2] + s1;
+        if( !( notYZ && notXY ) ) value[1] = value[1] + ( notXY ? s0 : s1 );
+    }
+    else if( scheme == 1 ) /* 4D :121-196 */
+    {
+        i32 hs = lsr( hash, 2 ), ig = imul( hs, 5 ), io = imul( hs, (i32)0xCCCCCCCDu );
+        io = imul( io & (i32)0xE0000003u, 3 | ( 1 << 27 ) );
+        float g[4];
+        gop4_direction( ig, g );
+        m *= fmaf( g[3], f[3], fmaf( g[2], f[2], fmaf( g[1], f[1], g[0] * f[0] ) ) );
+        gop4_direction( io, g );
+        for( int k = 0; k < 4; k++ ) value[k] = fmaf( m, g[k], value[k] );
+    }
+    else if( dim == 2 ) /* OrthogonalGradientMatrix 2D :199-243 */
+    {
+        i32 index = imul( lsr( hash, 1 ), 3 ), ofThree = lsr( index, 30 );
+        float masked = index >= 0 ? SKEW2F : 0.0f;
+        float gX = fxor( ofThree != 0 ? masked + 1.0f : masked, shl( asr( index, 28 ), 31 ) );
+        float gY = fxor( ofThree != 1 ? masked + 1.0f : masked, shl( asr( index, 29 ), 31 ) );
+        value[0] = fmaf( m, fmaf( f[1], gY, f[0] * gX ), value[0] );
+        m = fxor( m, shl( hash, 31 ) );
+        value[1] = fmaf( m, fmaf( f[1], gX, -( f[0] * gY ) ), value[1] ); /* FMulSub */
+    }
+    else if( dim == 3 ) /* :245-322 */
+    {
+        const float kA = 2.224744871391589f, kB = -0.224744871391589f, kC = -1.0f, kDE = 1.0f, kF = 2.0f;
+        i32 hs = lsr( hash, 1 ), facet = imul( hs, (i32)0xAAAAAAABu ), permute2 = shl( facet, 29 ), permute3 = lsr( imul( hs, 3 ), 30 );
+        i32 sign0 = shl( facet, 31 ), sign1 = shl( facet, 30 ) & (i32)0x80000000u, notYZ = facet, notXY = shl( facet, 1 );
+        float comp[3][2] = { { kA, kB }, { kB, kA }, { kDE, kDE } }, other[3] = { kC, kC, kF }, val[3];
+        for( int r = 0; r < 3; r++ ) /* rows A, B, C of the facet basis */
+        {
+            float gX = sel_hi( notYZ, other[r], fxor( comp[r][0], sign0 ) );
+            float gY = sel_hi( notYZ | notXY, sel_hi( notXY, fxor( comp[r][1], sign1 ), fxor( comp[r][0], sign0 ) ), other[r] );
+            float gZ = sel_hi( notXY, other[r], fxor( comp[r][1], sign1 ) );
+            val[r] = fmaf( gZ, f[2], fmaf( f[1], gY, f[0] * gX ) );
+        }
+        float vAB = sel_hi( permute2, val[1], val[0] ), vBA = sel_hi( permute2, val[0], val[1] ), vC = val[2];
+        m = fxor( m, shl( hash, 31 ) );
+        value[0] = fmaf( m, permute3 == 0 ? vC : vAB, value[0] );
+        value[1] = fmaf( m, permute3 == 1 ? vC : ( permute3 == 2 ? vBA : vAB ), value[1] );
+        value[2] = fmaf( m, permute3 == 2 ? vC : vBA, value[2] );
+    }
+    else /* 4D :324-686 */
+    {
+        const float kIdxNegAB = -0.375999676691291f, kFillAB = 0.222726847849776f, kIdxPosD = -SKEW4F, kUnidxD = SKEW4F;
+        const float kToSingleAB = -0.124000323308709f, kToSingleD = 0.190983005625053f, kSingleToExtra = SKEW4F, kABToC = 0.437016024448821f, kToDiag = -ROOT2F;
+        i32 hs = lsr( hash, 2 ), basis = imul( hs, 5 ), permute3 = asr( imul( hs, (i32)0xD5555556u ), 29 ), permute8 = asr( basis, 24 );
+        i32 pos = basis & ( 0x03 << 27 ), neg = ( asr( basis, 2 ) & ( 0x03 << 27 ) ) ^ pos;
+        /* `indexBasis >= int32v( 0x10 << 27 )` compares with INT_MIN after the int32 broadcast: true for every lane */
+        int single = pos == neg;
+        if( basis < ( 0x04 << 27 ) ) pos = -1;
+        float offAB = kToSingleAB + kSingleToExtra, offD = kToSingleD + kSingleToExtra;
+        float idxNegAB = single ? kIdxNegAB + offAB : kIdxNegAB, fillAB = single ? kFillAB + offAB : kFillAB;
+        float idxNegC = single ? idxNegAB : idxNegAB + kABToC, fillC = single ? fillAB : fillAB + kABToC;
+        float idxPosD = single ? kIdxPosD + offD : kIdxPosD, unidxD = single ? kUnidxD + offD : kUnidxD;
+        int counter = -1;
+        float val[4] = { 0, 0, 0, 0 }; /* A, B, C, D */
+        for( int axis = 0; axis < 4; axis++ )
+        {
+            int indexedPos = pos == shl( axis, 27 ), indexed = indexedPos || neg == shl( axis, 27 );
+            float idxAB = indexedPos ? idxNegAB + 1.0f : idxNegAB, idxC = indexedPos ? idxNegC + 1.0f : idxNegC, idxD = !indexedPos ? idxPosD - 1.0f : idxPosD;
+            /* the diagonal correction moves A -> B -> C as indexed axes are consumed: on axis k component j takes it when counter == j - k - 1
+             * (component A on axis 0 unconditionally; components that cannot be reached on an axis never take it) */
+            float un[3] = { fillAB, fillAB, fillC };
+            static const int kWhen[4][3] = { { 99, 0, 0 }, { -2, -1, 0 }, { -3, -2, -1 }, { 0, -3, -2 } }; /* 99 = always, 0 = never */
+            for( int j = 0; j < 3; j++ ) if( kWhen[axis][j] == 99 || ( kWhen[axis][j] != 0 && counter == kWhen[axis][j] ) ) un[j] = un[j] + kToDiag;
+            float g[4] = { indexed ? idxAB : un[0], indexed ? idxAB : un[1], indexed ? idxC : un[2], indexed ? idxD : unidxD };
+            for( int j = 0; j < 4; j++ ) val[j] = axis == 0 ? g[j] * f[0] : fmaf( g[j], f[axis], val[j] );
+            if( indexed ) counter -= 1;
+        }
+        i32 ix = asr( permute8, 1 ), iy = iadd( iadd( ix, 1 ), permute3 ), iz = permute8 & 1;
+        iz = iadd( iadd( ix, 1 ), iz >= permute3 ? iadd( iz, 1 ) : iz );
+        i32 isum = iadd( iadd( ix, iy ), iz );
+        m = fxor( m, shl( hash, 31 ) );
+        i32 idx[3] = { ix, iy, iz };
+        for( int k = 0; k < 3; k++ ) value[k] = fmaf( m, sel_hi( shl( idx[k], 31 ), sel_hi( shl( idx[k], 30 ), val[3], val[1] ), sel_hi( shl( idx[k], 30 ), val[2], val[0] ) ), value[k] );
+        value[3] = fmaf( m, sel_hi( shl( isum, 31 ), sel_hi( shl( isum, 30 ), val[3], val[1] ), sel_hi( shl( isum, 30 ), val[0], val[2] ) ), value[3] );
+    }
 }
 
 /* ------------------------------------------------------------------ Cellular [Cellular.inl:18-807] */
@@ -923,9 +1086,39 @@ static float warp_gradient( const Node* n, i32 seed, float amp, int dim, const f
     return strength;
 }
 
+/* DomainWarpSimplex / DomainWarpSuperSimplex::Warp [DomainWarpSimplex.inl:728-1088, 1091-1836] */
+static float warp_simplex( const Node* n, i32 seed, float amp, int dim, const float* scaled, float* out )
+{
+    int super = n->id == N_DomainWarpSuperSimplex, scheme = n->i[0] == 1 ? 1 : 0;
+    static const float kBound[2][3][2] = {
+        { { 70.1480577066486f, (float)( 49.918426513671875 / 2.0 ) }, { 16.281631889139874f, (float)( 32.69428253173828125 / 1.4142135623730951 ) },
+          { 30.88161777516092f, (float)( 33.653125584827855 / 1.4142135623730951 ) } },
+        { { 12.814453124999995f, (float)( 9.28993664146183 / 2.0 ) }, { 37.63698669623629f, (float)( 144.736422163332608 / 1.4142135623730951 ) },
+          { 48.80058117543753f, (float)( 115.21625311930542 / 1.4142135623730951 ) } } };
+    if( !super ) seed = iadd( seed, n->seedOffset ); /* only DomainWarpSimplex::Warp adds the offset itself [:733 vs :1094] */
+    Vert v[16];
+    int count = super ? supersimplex_vertices( seed, dim, scaled, v ) : simplex_vertices( seed, dim, scaled, v );
+    float value[4] = { 0, 0, 0, 0 };
+    for( int k = 0; k < count; k++ ) vec_contribution( scheme, dim, v[k].hash, v[k].d, v[k].falloff, value );
+    if( dim == 3 && scheme != 0 ) /* match gradient orientation [:911-917, 1426-1433] */
+    {
+        float delta = ( super ? (float)( -2.0 / 3.0 ) : (float)( -2.0 / 2.0 ) ) * ( value[0] + value[1] + value[2] );
+        for( int k = 0; k < 3; k++ ) value[k] += delta;
+    }
+    for( int k = 0; k < dim; k++ )
+    {
+        value[k] *= kBound[super][dim - 2][scheme] * n->f[k];
+        out[k] = fmaf( value[k], amp, out[k] );
+    }
+    float strength = value[0] * value[0];
+    for( int k = 1; k < dim; k++ ) strength = fmaf( value[k], value[k], strength );
+    return strength;
+}
+
 static float warp_call( const Node* warpNode, i32 seed, float amp, int dim, const float* scaled, float* out )
 {
-    return warp_gradient( warpNode, seed, amp, dim, scaled, out ); /* only DomainWarpGradient is restated */
+    if( warpNode->id == N_DomainWarpGradient ) return warp_gradient( warpNode, seed, amp, dim, scaled, out );
+    return warp_simplex( warpNode, seed, amp, dim, scaled, out );
 }
 
 /* ------------------------------------------------------------------ the recursive evaluator */
@@ -975,7 +1168,7 @@ static float eval( const Node* n, i32 seed, int dim, const float* pin )
         static const float kBound[5] = { 0, 0, 0.0261208079755306243896484375f, 0.030586399137973785400390625f, 0.036730043590068817138671875f };
         seed = iadd( seed, n->seedOffset );
         for( int d = 0; d < dim; d++ ) p[d] *= n->freq;
-        float v = dim == 2 ? noise_simplex2( seed, p[0], p[1] ) : ( dim == 3 ? noise_simplex3( seed, p[0], p[1], p[2] ) : noise_simplex4( seed, p ) );
+        float v = noise_simplex( seed, dim, p );
         return range_out( n, v, -kBound[dim], kBound[dim] );
     }
     case N_SuperSimplex:
@@ -983,7 +1176,7 @@ static float eval( const Node* n, i32 seed, int dim, const float* pin )
         static const float kBound[5] = { 0, 0, 0.14084912836551666259765625f, 0.0069091119803488254547119140625f, (float)0.011310013942420482635498046875 };
         seed = iadd( seed, n->seedOffset );
         for( int d = 0; d < dim; d++ ) p[d] *= n->freq;
-        float v = dim == 2 ? noise_supersimplex2( seed, p[0], p[1] ) : ( dim == 3 ? noise_supersimplex3( seed, p[0], p[1], p[2] ) : noise_supersimplex4( seed, p ) );
+        float v = noise_supersimplex( seed, dim, p );
         return range_out( n, v, -kBound[dim], kBound[dim] );
     }
     case N_Perlin:
@@ -1029,7 +1222,9 @@ static float eval( const Node* n, i32 seed, int dim, const float* pin )
         t -= floorf( t * 0.5f ) * 2.0f;
         return t < 1.0f ? t : 2.0f - t;
     }
-    case N_DomainWarpGradient: /* DomainWarp::GenT, DomainWarp.inl:9-17 (the offset is added here AND inside Warp) */
+    case N_DomainWarpSimplex:
+    case N_DomainWarpSuperSimplex:
+    case N_DomainWarpGradient: /* DomainWarp::GenT, DomainWarp.inl:9-17 (Gradient and Simplex add the offset again inside Warp) */
     {
         i32 sourceSeed = seed;
         float scaled[4];

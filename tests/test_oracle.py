@@ -80,10 +80,11 @@ def test_port_oracle_vs_strict_ref_every_node(ref):
         pytest.skip("oracle/libfn2oracle.so not built")
     checked = 0
     for hybrid_nodes in (False, True):
-        for node_id in range(47):
-            if node_id in (16, 17):
-                continue
-            text = default_tree(node_id, hybrid_nodes).encode()
+        for node_id in list(range(47)) + [16, 17]:  # second visit of the simplex warps: GradientOuterProduct scheme
+            tree = default_tree(node_id, hybrid_nodes)
+            if node_id in (16, 17) and checked >= 47 * 3 * (1 + hybrid_nodes):
+                tree.variables["Vectorization Scheme"] = 1
+            text = tree.encode()
             a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
             assert a.supported, node_id
             for got, want in ((a.grid2d(-3.3, 2.1, 40, 40, 1.9, 1.9, 1337)[0], b.grid2d(-3.3, 2.1, 40, 40, 1.9, 1.9, 1337)[0]),
@@ -92,7 +93,7 @@ def test_port_oracle_vs_strict_ref_every_node(ref):
                 same = np.array_equal(got.view(np.uint32), want.view(np.uint32)) or (np.isnan(got).all() and np.isnan(want).all())
                 assert same, (node_id, hybrid_nodes, helpers.compare(got, want))
                 checked += 1
-    assert checked == 45 * 2 * 3
+    assert checked == 49 * 2 * 3
 
 
 def test_port_oracle_slab_rows_equal_whole_grid():
