@@ -41,6 +41,7 @@ WORKLOADS = {
     "c5": dict(tree="c5_supersimplex", kind="pos4d", n=(256 * 1024 * 1024,), step=0.0, ops=843, desc="SuperSimplex GenPositionArray4D 256Mi positions U[-1000,1000)^4 (Philox key 1337)"),
 }
 SEED = 1337
+MATH_MODES = {"strict": 0, "relaxed": 1, "strict_generic": 2, "relaxed_generic": 3}
 
 
 def parse_args():
@@ -53,7 +54,7 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of one CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--math", default="strict", choices=["strict", "relaxed"])
+    p.add_argument("--math", default="strict", choices=sorted(MATH_MODES), help="fnb200SetMathMode: strict/relaxed arithmetic x table/generic gradient flavour")
     return p.parse_args()
 
 
@@ -232,7 +233,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not fn.device_available():
         raise SystemExit("fastnoise2_b200: no usable CUDA device: " + fn.last_error())
-    fn.set_math_mode(1 if args.math == "relaxed" else 0)
+    fn.set_math_mode(MATH_MODES[args.math])
     lib = fn.lib
     gen = fn.Generator(fn.TREES[w["tree"]])
     stream = torch.cuda.Stream()  # the stream every kernel of the timed region is launched on, and the events are recorded on

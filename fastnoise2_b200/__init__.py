@@ -6,3 +6,4 @@ through the C ABI declared in include/FastNoise/FastNoise_C.h and FastNoise_B200
 """
 from . import _lib
 from .api import Generator, lib, TREES, device_available, last_error, set_math_mode  # noqa: F401
+from .api import MATH_STRICT, MATH_RELAXED, MATH_STRICT_GENERIC, MATH_RELAXED_GENERIC  # noqa: F401

@@ -31,7 +31,11 @@ def last_error():
     return lib.fnb200LastError().decode()
 
 
+MATH_STRICT, MATH_RELAXED, MATH_STRICT_GENERIC, MATH_RELAXED_GENERIC = 0, 1, 2, 3
+
+
 def set_math_mode(mode):
+    """fnb200SetMathMode: bit 0 = relaxed arithmetic, bit 1 = generic (non-table) gradient flavour; see FastNoise_B200.h."""
     lib.fnb200SetMathMode(int(mode))
 
 

@@ -114,7 +114,7 @@ namespace
         std::vector<std::string> o = {
             "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
             "-DFN2_BLOCK=" + std::to_string( kBlock ),
-            mathMode ? "--fmad=true" : "--fmad=false",
+            ( mathMode & 1 ) ? "--fmad=true" : "--fmad=false",
         };
         if( const char* extra = std::getenv( "FASTNOISE2_B200_NVRTC_FLAGS" ) )
         {
@@ -197,7 +197,7 @@ namespace
 
     const Module* LoadModule( const std::string& source, int mathMode, int device, std::string& error )
     {
-        const std::uint64_t hash = Fnv64( source, Fnv64( mathMode ? "relaxed" : "strict" ) );
+        const std::uint64_t hash = Fnv64( source, Fnv64( "math mode " + std::to_string( mathMode ) ) );
         std::lock_guard<std::mutex> lock( gModuleMutex );
         auto it = gModules.find( { hash, device } );
         if( it != gModules.end() ) return &it->second;
@@ -351,7 +351,7 @@ namespace FastNoise
         void SetLastError( const std::string& message ) { tLastError = message; }
         const std::string& LastError() { return tLastError; }
         int MathMode() { return gMathMode.load(); }
-        void SetMathMode( int mode ) { gMathMode.store( mode ? 1 : 0 ); }
+        void SetMathMode( int mode ) { gMathMode.store( mode & 3 ); }
         unsigned long long LaunchCount() { return gLaunches.load(); }
         void CountLaunch() { gLaunches.fetch_add( 1, std::memory_order_relaxed ); }
 

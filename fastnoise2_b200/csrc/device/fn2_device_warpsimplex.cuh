@@ -1,5 +1,5 @@
 // fastnoise2_b200 -- device node library: DomainWarpSimplex / DomainWarpSuperSimplex displacement fields.
-// Restates include/FastNoise/Generators/DomainWarpSimplex.inl (generic, non-table code paths): the lattice
+// Restates include/FastNoise/Generators/DomainWarpSimplex.inl (both flavours, see FN2_TABLES in fn2_device.cuh): the lattice
 // geometry is the Simplex / SuperSimplex vertex list (fn2_device.cuh, fn2_device_supersimplex.cuh); each vertex
 // contributes a VECTOR built from its hash by one of two schemes
 //   SCHEME 0  OrthogonalGradientMatrix  [:199-686]
@@ -25,6 +25,15 @@ namespace fn2
         i32 hashShifted = lsr( hash31, 1 );
         i32 indexGradient = imul( hashShifted, 12 >> 2 );                                  // [0,12) in the upper four bits
         i32 indexOuter = imul( hashShifted, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;          // [0,12) in bits 0,1,30,31
+#if FN2_TABLES
+        // [:13-25]
+        const float* g = sGradientTables + kTabGop2 + ( ( indexGradient >> 28 ) & 15 );
+        const float* o = sGradientTables + kTabGop2 + ( ( indexOuter | ( indexOuter >> 28 ) ) & 15 );
+        multiplier *= fma_( fY, g[16], fX * g[0] );
+        valueX = fma_( multiplier, o[0], valueX );
+        valueY = fma_( multiplier, o[16], valueY );
+        return;
+#endif
         {
             float u = sel_hi( shl( indexGradient, 2 ), fY, fX );
             float v = sel_hi( shl( indexGradient, 2 ), fX, fY );
@@ -48,6 +57,16 @@ namespace fn2
         i32 indexGradient = lsr( imul( hashShifted, 12 >> 2 ), 28 );                        // [0,12)
         i32 indexOuter = imul( hashShifted, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
         indexOuter |= indexOuter >> 28;
+#if FN2_TABLES
+        // [:70-81] the 12 directions are the first 12 entries of the common 3D gradient table
+        const float* g = sGradientTables + kTabCommon3 + indexGradient;
+        const float* o = sGradientTables + kTabCommon3 + ( indexOuter & 15 );
+        multiplier *= fma_( g[32], fZ, fma_( fY, g[16], fX * g[0] ) );
+        valueX = fma_( multiplier, o[0], valueX );
+        valueY = fma_( multiplier, o[16], valueY );
+        valueZ = fma_( multiplier, o[32], valueZ );
+        return;
+#endif
         {
             float u = indexGradient >= 8 ? fY : fX;
             float v = indexGradient >= 4 ? fZ : fY;
@@ -179,11 +198,18 @@ namespace fn2
         i32 indexNegative = ( indexBasis >> 2 ) & ( 0x03 << 27 );
         indexNegative ^= indexPositive;
 
+        bool singleCase = indexPositive == indexNegative;
+#if FN2_TABLES
+        // [:370-460] the 32-entry tables carry the "extra" constants in entries 16-19 only, i.e. the comparison as it was meant;
+        // every other entry is what the select logic below produces, so the tables are not materialised here.
+        const bool extraCase = lsr( indexBasis, 27 ) >= 16;
+        bool singleNonExtraCase = singleCase && !extraCase;
+#else
         // `indexBasis >= int32v( 0x10 << 27 )`: the literal is 2^31, which the int32 broadcast turns into INT_MIN, so the signed
         // comparison holds for every lane. Reproduced as is (the reference's AVX2 branch has the same expression).
         const bool extraCase = true;
-        bool singleCase = indexPositive == indexNegative;
         bool singleNonExtraCase = indexBasis < ( 0x04 << 27 );
+#endif
         if( singleNonExtraCase ) indexPositive = -1; // forces the indexPositive checks to fail
 
         float singleOffsetAB = extraCase ? kToSingleAB + kSingleToExtra : kToSingleAB;

@@ -20,6 +20,7 @@ namespace
 extern "C" __global__ void __launch_bounds__( 256 ) fn2_device_check( float* __restrict__ out, int n, int which, int seed, float step )
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
+    fn2::stage_tables();
     if( i >= n ) return;
     const float x = i * step, y = x * 0.7f, z = x * 0.3f, w = x * 0.1f;
     float v = 0;

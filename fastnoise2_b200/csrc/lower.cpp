@@ -690,6 +690,7 @@ namespace
           << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.total;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    fn2::stage_tables();\n"
           << "    if( valid )\n    {\n"
           << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
           << "        const unsigned ix = first - rowLocal * (unsigned)a.count[0];\n"
@@ -736,6 +737,7 @@ namespace
           << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.total;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    fn2::stage_tables();\n"
           << "    if( valid )\n    {\n"
           << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
           << "        const unsigned ix = first - rowLocal * (unsigned)a.xSize;\n"
@@ -767,6 +769,7 @@ namespace
           << "    const unsigned long long first = ( (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.count;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    fn2::stage_tables();\n"
           << "    if( valid )\n    {\n"
           << "        const bool full = first + " << ppt << "u <= a.count;\n"
           << "        float in[" << dim << "][" << ppt << "];\n"
@@ -837,8 +840,9 @@ namespace FastNoise
 
             std::ostringstream src;
             src << "// generated by fastnoise2_b200 -- entry kind " << entryKind << ", " << pointsPerThread << " point(s) per thread, "
-                << ( mathMode ? "relaxed" : "strict" ) << " math\n"
-                << "#define FN2_RELAXED " << ( mathMode ? 1 : 0 ) << "\n"
+                << ( ( mathMode & 1 ) ? "relaxed" : "strict" ) << " math, " << ( ( mathMode & 2 ) ? "generic" : "table" ) << " gradients\n"
+                << "#define FN2_RELAXED " << ( mathMode & 1 ) << "\n"
+                << "#define FN2_TABLES " << ( ( mathMode & 2 ) ? 0 : 1 ) << "\n"
                 << "#ifndef FN2_BLOCK\n#define FN2_BLOCK 256\n#endif\n"
                 << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP\n#endif\n"
                 << "#include \"fn2_device.cuh\"\n\n"

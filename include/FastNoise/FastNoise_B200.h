@@ -36,9 +36,15 @@ FASTNOISE_API const char* fnb200LastError( void );
 /* 1 if a usable CUDA device (compute capability 10.x) and NVRTC are present. Never throws. */
 FASTNOISE_API int fnb200DeviceAvailable( void );
 
-/* Numerics mode for trees compiled AFTER the call (process-wide):
- *   0 = strict  : no FMA contraction beyond the reference's explicit FMulAdd sites, IEEE div/sqrt (default; parity mode)
- *   1 = relaxed : nvcc FMA contraction on, approximate rsqrt/rcp where the reference's RELAXED build uses them */
+/* Numerics mode for trees compiled AFTER the call (process-wide). Two independent bits:
+ *   bit 0  0 = strict  : no FMA contraction beyond the reference's explicit FMulAdd sites, IEEE div/sqrt (parity mode)
+ *          1 = relaxed : nvcc FMA contraction on, approximate rsqrt/rcp where the reference's RELAXED build uses them
+ *   bit 1  0 = table gradients   : the reference's AVX512_F code path (permute tables; Utils.inl:124,167,196 and
+ *                                  DomainWarpSimplex.inl:13,70,126,198,254,370), tables staged in shared memory
+ *          1 = generic gradients : the select/xor code path its non-AVX-512 levels run
+ * The two gradient flavours round differently (the reference's own output differs between its ISA levels in the same
+ * way); each is bit-exact against the corresponding build of the reference sources. Default 0 = strict + tables. */
+enum fnb200_math_mode { FNB200_MATH_STRICT = 0, FNB200_MATH_RELAXED = 1, FNB200_MATH_STRICT_GENERIC = 2, FNB200_MATH_RELAXED_GENERIC = 3 };
 FASTNOISE_API int fnb200SetMathMode( int mode );
 FASTNOISE_API int fnb200GetMathMode( void );
 

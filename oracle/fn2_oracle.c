@@ -379,23 +379,48 @@ static i32 hash_primes( i32 seed, const i32* p, int dim ) { u32 h = (u32)xor_pri
 static i32 hash_hb( i32 seed, const i32* p, int dim ) { return (i32)( (u32)xor_primed( seed, p, dim ) * HASH_MUL ); }                                /* Utils.inl:232 */
 static float value_coord( i32 seed, const i32* p, int dim ) { u32 h = (u32)xor_primed( seed, p, dim ); h *= h * HASH_MUL; return (float)(i32)h; }     /* Utils.inl:242 */
 
-/* gradient dot products, generic code path */
-static float grad2( i32 h, float x, float y ) /* Utils.inl:181-190 */
+/* gradient dot products.
+ * The reference has two FLAVOURS of every gradient helper, picked at compile time by `if constexpr( SIMD & FeatureFlag::... )`:
+ *   generic (gTables = 0): select + sign-xor forms -- what its Scalar/NEON/WASM (and, for most helpers, SSE/AVX2) levels run;
+ *   tables  (gTables = 1): the AVX512_F branches -- a 16/32-entry weight table indexed by the hash, then one FMA chain.
+ * They round differently (a table weight multiplies inside the chain), so each flavour is its own parity target:
+ * oracle/_ref/libfn2ref_strict_avx2.so pins the first, libfn2ref_strict_avx512.so the second. */
+static int gTables = 0;
+void fn2oSetFlavor( int tables ) { gTables = tables != 0; }
+int fn2oGetFlavor( void ) { return gTables; }
+
+#define R2P1 ( 1.0f + (float)1.4142135623730950488016887242097 )
+static const float kPerlin2X[8] = { R2P1, -R2P1, R2P1, -R2P1, 1, -1, 1, -1 };            /* Utils.inl:169, low 3 index bits (the table repeats) */
+static const float kPerlin2Y[8] = { 1, 1, -1, -1, R2P1, R2P1, -R2P1, -R2P1 };            /* Utils.inl:170 */
+static const float kCommon3[3][16] = {                                                    /* Utils.inl:126-128 */
+    { 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0, 1, 0, -1, 0 },
+    { 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1 },
+    { 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1, 0, 1, 0, -1 } };
+static const float kPerlin4[4][32] = {                                                    /* Utils.inl:198-201, entries 0-15 = first operand, 16-31 = second */
+    { 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1,   1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1 },
+    { 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0,   1, 1, -1, -1, 1, 1, -1, -1, 1, 1, -1, -1, 1, 1, -1, -1 },
+    { 1, 1, -1, -1, 1, 1, -1, -1, 1, 1, -1, -1, 1, 1, -1, -1,   0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, -1, -1, -1, -1 },
+    { 1, 1, 1, 1, -1, -1, -1, -1, 1, 1, 1, 1, -1, -1, -1, -1,   1, 1, 1, 1, -1, -1, -1, -1, 0, 0, 0, 0, 0, 0, 0, 0 } };
+
+static float grad2( i32 h, float x, float y ) /* Utils.inl:162-190 */
 {
+    if( gTables ) return fmaf( kPerlin2X[h & 7], x, y * kPerlin2Y[h & 7] );
     x = fxor( x, shl( h, 31 ) ); y = fxor( y, shl( asr( h, 1 ), 31 ) );
     int swap = shl( h, 29 ) < 0;
-    return fmaf( 1.0f + (float)1.4142135623730950488016887242097, swap ? y : x, swap ? x : y );
+    return fmaf( R2P1, swap ? y : x, swap ? x : y );
 }
-static float grad3( i32 h, float x, float y, float z ) /* Utils.inl:132-158 */
+static float grad3( i32 h, float x, float y, float z ) /* Utils.inl:121-158 */
 {
+    if( gTables ) return fmaf( kCommon3[0][h & 15], x, fmaf( y, kCommon3[1][h & 15], z * kCommon3[2][h & 15] ) );
     i32 a = h & 13;
     float u = a > 7 ? y : x;
     float v = a == 12 ? x : z;
     if( a < 2 ) v = y;
     return fxor( u, shl( h, 31 ) ) + fxor( v, shl( asr( h, 1 ), 31 ) );
 }
-static float grad4( i32 h, float x, float y, float z, float w ) /* Utils.inl:205-218 */
+static float grad4( i32 h, float x, float y, float z, float w ) /* Utils.inl:193-218 */
 {
+    if( gTables ) return fmaf( kPerlin4[0][h & 31], x, fmaf( y, kPerlin4[1][h & 31], fmaf( z, kPerlin4[2][h & 31], w * kPerlin4[3][h & 31] ) ) );
     i32 p = h & ( 3 << 3 );
     float a = p > 0 ? x : y, b = shl( h, 27 ) < 0 ? y : z, c = p > ( 2 << 3 ) ? z : w;
     return fxor( a, shl( h, 31 ) ) + fxor( b, shl( asr( h, 1 ), 31 ) ) + fxor( c, shl( asr( h, 2 ), 31 ) );
@@ -809,7 +834,26 @@ static void gop4_direction( i32 index, float* g ) /* :149-166 */
 
 static void vec_contribution( int scheme, int dim, i32 hash, const float* f, float m, float* value )
 {
-    if( scheme == 1 && dim == 2 ) /* GradientOuterProduct 2D :7-60 */
+    /* tables flavour [:13-25, :70-81]: 12 directions in the low entries of a 16-entry table, one FMA chain */
+    static const float kGop2X[12] = { ROOT3F, -ROOT3F, 1, -1, ROOT3F, -ROOT3F, -1, 1, 2, -2, 0, 0 };
+    static const float kGop2Y[12] = { 1, -1, ROOT3F, -ROOT3F, -1, 1, ROOT3F, -ROOT3F, 0, 0, 2, -2 };
+    static const float kGop3[3][12] = { { 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0 }, { 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1 }, { 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1 } };
+    if( gTables && scheme == 1 && dim == 2 )
+    {
+        i32 hs = lsr( hash, 1 ), ig = asr( imul( hs, 3 ), 28 ) & 15, io = imul( hs, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
+        io = ( io | asr( io, 28 ) ) & 15;
+        m *= fmaf( f[1], kGop2Y[ig], f[0] * kGop2X[ig] );
+        value[0] = fmaf( m, kGop2X[io], value[0] );
+        value[1] = fmaf( m, kGop2Y[io], value[1] );
+    }
+    else if( gTables && scheme == 1 && dim == 3 )
+    {
+        i32 hs = lsr( hash, 1 ), ig = lsr( imul( hs, 3 ), 28 ), io = imul( hs, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
+        io = ( io | asr( io, 28 ) ) & 15;
+        m *= fmaf( kGop3[2][ig], f[2], fmaf( f[1], kGop3[1][ig], f[0] * kGop3[0][ig] ) );
+        for( int k = 0; k < 3; k++ ) value[k] = fmaf( m, kGop3[k][io], value[k] );
+    }
+    else if( scheme == 1 && dim == 2 ) /* GradientOuterProduct 2D :7-60 */
     {
         i32 hs = lsr( hash, 1 ), ig = imul( hs, 3 ), io = imul( hs, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;
         float u = sel_hi( shl( ig, 2 ), f[1], f[0] ), v = sel_hi( shl( ig, 2 ), f[0], f[1] );
@@ -878,10 +922,12 @@ static void vec_contribution( int scheme, int dim, i32 hash, const float* f, flo
         const float kToSingleAB = -0.124000323308709f, kToSingleD = 0.190983005625053f, kSingleToExtra = SKEW4F, kABToC = 0.437016024448821f, kToDiag = -ROOT2F;
         i32 hs = lsr( hash, 2 ), basis = imul( hs, 5 ), permute3 = asr( imul( hs, (i32)0xD5555556u ), 29 ), permute8 = asr( basis, 24 );
         i32 pos = basis & ( 0x03 << 27 ), neg = ( asr( basis, 2 ) & ( 0x03 << 27 ) ) ^ pos;
-        /* `indexBasis >= int32v( 0x10 << 27 )` compares with INT_MIN after the int32 broadcast: true for every lane */
-        int single = pos == neg;
-        if( basis < ( 0x04 << 27 ) ) pos = -1;
-        float offAB = kToSingleAB + kSingleToExtra, offD = kToSingleD + kSingleToExtra;
+        /* generic flavour: `indexBasis >= int32v( 0x10 << 27 )` compares with INT_MIN after the int32 broadcast, true for every lane.
+         * tables flavour [:370-460]: the 32-entry tables hold the "extra" constants only in entries 16-19, i.e. the comparison as meant;
+         * everything else in the tables is what the select logic below yields (checked against libfn2ref_strict_avx512.so). */
+        int single = pos == neg, extra = gTables ? lsr( basis, 27 ) >= 16 : 1;
+        if( gTables ? !extra && single : basis < ( 0x04 << 27 ) ) pos = -1;
+        float offAB = extra ? kToSingleAB + kSingleToExtra : kToSingleAB, offD = extra ? kToSingleD + kSingleToExtra : kToSingleD;
         float idxNegAB = single ? kIdxNegAB + offAB : kIdxNegAB, fillAB = single ? kFillAB + offAB : kFillAB;
         float idxNegC = single ? idxNegAB : idxNegAB + kABToC, fillC = single ? fillAB : fillAB + kABToC;
         float idxPosD = single ? kIdxPosD + offD : kIdxPosD, unidxD = single ? kUnidxD + offD : kUnidxD;

@@ -15,6 +15,7 @@ extern "C"
 {
     int fn2refLanes() { return FN2SHIM_LANES; }
     int fn2refRelaxed() { return FN2SHIM_RELAXED; }
+    int fn2refTables() { return FN2SHIM_AVX512_PATHS; } // 1: the reference's AVX512_F gradient-table branches are live
 
     // Generates nx*ny*nz points (row-major, x fastest) into out, splitting z (or y when nz==1)
     // into `threads` contiguous slabs, each through the ordinary fnGenUniformGrid3D/2D call with a

@@ -16,8 +16,13 @@
 //           default build flags (src/CMakeLists.txt:65-69,96-102). Used for CPU TIMING only.
 // Lanes: FN2SHIM_LANES = 8 (AVX2+FMA, one ymm) or 16 (AVX-512F, one zmm).
 //
-// Every `if constexpr( SIMD & FeatureFlag::X )` in the node sources takes the generic branch
-// (operator& below is always false): that is the code path FastSIMD's Scalar/NEON/WASM levels run.
+// Two FLAVOURS of the node sources' `if constexpr( SIMD & FeatureFlag::X )` chains:
+//   generic (FN2SHIM_AVX512_PATHS=0): every flag reads false -- the select/xor code path FastSIMD's
+//           Scalar/NEON/WASM levels run.
+//   tables  (FN2SHIM_AVX512_PATHS=1, 16 lanes): FeatureFlag::AVX512_F reads true -- the permute-table
+//           gradient forms an AVX-512 build of the reference runs (Utils.inl:38,84,124,167,196 and
+//           DomainWarpSimplex.inl:13,70,126,198,254,370). The two flavours round differently (a table
+//           weight multiplies inside the FMA chain), so each is its own parity target.
 //
 // Semantics that cannot be checked against upstream here ("parity unpinned"):
 //   Convert<int32>(float) = round-to-nearest-even (cvtps2dq); Min/Max = x86 minps/maxps operand
@@ -47,8 +52,17 @@ namespace FastSIMD
     enum class FeatureFlag : std::uint32_t { Scalar = 1, x86 = 2, SSE41 = 4, AVX = 8, AVX2 = 16, AVX512_F = 32 };
     enum class FeatureSet : std::uint32_t { Invalid = 0, SHIM = 1, Max = ~0u };
 
+#ifndef FN2SHIM_AVX512_PATHS
+#define FN2SHIM_AVX512_PATHS 0
+#endif
+#if FN2SHIM_AVX512_PATHS
+    // "tables" flavour: exactly the AVX512_F branches (the 11 gradient-table sites of Utils.inl and
+    // DomainWarpSimplex.inl); every other flag sits in an else-branch of those chains or guards a vzeroupper.
+    constexpr bool operator&( FeatureSet, FeatureFlag f ) { return f == FeatureFlag::AVX512_F; }
+#else
     // generic code path everywhere
     constexpr bool operator&( FeatureSet, FeatureFlag ) { return false; }
+#endif
     constexpr FeatureSet FeatureSetDefault() { return FeatureSet::SHIM; }
     constexpr bool IsRelaxed() { return FN2SHIM_RELAXED != 0; }
 

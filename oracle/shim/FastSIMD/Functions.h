@@ -200,9 +200,28 @@ namespace FS
     FS_FORCEINLINE f32v Modulus( f32v a, f32v b ) { return FNMulAdd( f32v( n_trunc( ( a / b ).v ), 0 ), b, a ); }
     FS_FORCEINLINE i32v Modulus( i32v a, i32v b ) { return i32v( a.v % b.v, 0 ); }
 
-    // ---------------------------------------------------------------- names that only appear inside discarded x86 branches
+    // ---------------------------------------------------------------- ISA-specific branches
+#if FN2SHIM_AVX512_PATHS
+    // "tables" flavour: the node sources' AVX512_F branches are live. They build 16-entry lane tables with
+    // FS::Constant and index them with the real _mm512_permutexvar_ps / _mm512_permutex2var_ps / _mm512_rol_epi32
+    // intrinsics through FS::NativeExec; a 16-lane GCC vector IS a zmm register, so the arguments are only re-typed.
+    static_assert( kLanes == 16, "the AVX512_F code paths index 16-entry tables: build with FN2SHIM_LANES=16" );
+    template<typename T, typename... A>
+    FS_FORCEINLINE Register<T, kLanes> Constant( A... a )
+    {
+        static_assert( sizeof...( A ) == kLanes, "one table entry per lane" );
+        typename VecOf<T>::type v = { (T)a... };
+        return Register<T, kLanes>( v, 0 );
+    }
+    FS_FORCEINLINE __m512 Fn2Native( f32v a ) { return (__m512)a.v; }
+    FS_FORCEINLINE __m512i Fn2Native( i32v a ) { return (__m512i)a.v; }
+    template<typename R, typename F, typename... A>
+    FS_FORCEINLINE R NativeExec( F&& f, A... a ) { return R( (typename R::Vec)f( Fn2Native( a )... ), 0 ); }
+#else
+    // generic flavour: these names only appear inside discarded `if constexpr` branches
     template<typename T, typename... A>
     Register<T, kLanes> Constant( A... ) { return {}; }
     template<typename R, typename F, typename... A>
     R NativeExec( F&&, A&&... ) { return {}; }
+#endif
 }

@@ -1,5 +1,6 @@
-"""Regenerates tests/golden/*.npz and metadata.json from the STRICT oracle build of the reference
-(oracle/_ref/libfn2ref_strict_avx2.so = the reference's own node sources over oracle/shim). Run in the build
+"""Regenerates tests/golden/*.npz and metadata.json from the STRICT oracle builds of the reference
+(oracle/_ref/libfn2ref_strict_avx2.so / _avx512.so = the reference's own node sources over oracle/shim, generic / table
+gradient flavour -> outputs.npz / outputs_tables.npz). Run in the build
 container, where /root/reference exists:   make -C oracle && python tests/golden/make_golden.py
 The reference's own tests hold no expected values, so these vectors pin the oracle's
 semantics, not Auburn's binaries -- "parity unpinned" upstream, see DESIGN.md.
@@ -43,18 +44,20 @@ def dump_metadata(lib):
 
 
 def main():
-    ref = helpers.load_ref("strict_avx2")
-    assert ref is not None, "build oracle/_ref first"
-    json.dump(dump_metadata(ref), open(os.path.join(HERE, "metadata.json"), "w"), indent=1)
-    arrays = {}
-    summary = {}
-    for name, case in GOLDEN_CASES.items():
-        out, mm = run_case(helpers.RefNode(ref, case["tree"]), case)
-        arrays[name] = out
-        summary[name] = {"min": float(mm[0]), "max": float(mm[1]), "fnv1a": "%08x" % helpers.fnv1a_words(out), "n": int(out.size)}
-        print(name, summary[name])
-    np.savez_compressed(os.path.join(HERE, "outputs.npz"), **arrays)
-    json.dump(summary, open(os.path.join(HERE, "summary.json"), "w"), indent=1)
+    for variant, suffix in (("strict_avx2", ""), ("strict_avx512", "_tables")):  # generic / table gradient flavour
+        ref = helpers.load_ref(variant)
+        assert ref is not None, "build oracle/_ref first (and run on a CPU with AVX-512 for the table flavour)"
+        if not suffix:
+            json.dump(dump_metadata(ref), open(os.path.join(HERE, "metadata.json"), "w"), indent=1)
+        arrays = {}
+        summary = {}
+        for name, case in GOLDEN_CASES.items():
+            out, mm = run_case(helpers.RefNode(ref, case["tree"]), case)
+            arrays[name] = out
+            summary[name] = {"min": float(mm[0]), "max": float(mm[1]), "fnv1a": "%08x" % helpers.fnv1a_words(out), "n": int(out.size)}
+            print(variant, name, summary[name])
+        np.savez_compressed(os.path.join(HERE, "outputs%s.npz" % suffix), **arrays)
+        json.dump(summary, open(os.path.join(HERE, "summary%s.json" % suffix), "w"), indent=1)
 
 
 if __name__ == "__main__":

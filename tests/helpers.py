@@ -20,7 +20,8 @@ def cpu_flags():
 
 
 def load_ref(variant):
-    """variant: strict_avx2 | relaxed_avx2 | relaxed_avx512. Returns a bound ctypes library or None."""
+    """variant: strict_avx2 | strict_avx512 | relaxed_avx2 | relaxed_avx512 (avx2 = generic gradient flavour, avx512 = table
+    flavour). Returns a bound ctypes library, or None when it is not built or this CPU cannot run it."""
     from fastnoise2_b200 import _lib
     path = os.path.join(REF_DIR, "libfn2ref_%s.so" % variant)
     if not os.path.exists(path):
@@ -132,11 +133,12 @@ class ProductNode:
         return out, np.array(self.gen.positions(out, pos, offsets, seed), np.float32)
 
 
-def load_golden():
+def load_golden(suffix=""):
+    """suffix "" = generic gradient flavour, "_tables" = table flavour (tests/conftest.py FLAVOURS)."""
     import json
     golden_dir = os.path.join(ROOT, "tests", "golden")
-    outputs = np.load(os.path.join(golden_dir, "outputs.npz"))
-    summary = json.load(open(os.path.join(golden_dir, "summary.json")))
+    outputs = np.load(os.path.join(golden_dir, "outputs%s.npz" % suffix))
+    summary = json.load(open(os.path.join(golden_dir, "summary%s.json" % suffix)))
     metadata = json.load(open(os.path.join(golden_dir, "metadata.json")))
     return outputs, summary, metadata
 

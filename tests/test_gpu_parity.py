@@ -3,6 +3,8 @@
 Bar: every output word bit-identical to the strict oracle (same operation sequence, FMAs only where the reference
 has them, IEEE div/sqrt) -- which subsumes "integer hashes and cell selection bit-exact" -- with a float tolerance of
 2e-5 absolute stated for the relaxed math mode (FMA contraction, measured envelope 9.1e-6: SURVEY.md 8d).
+Every test that takes `ref` or `flavour` runs twice: table gradients (product default) against the reference's AVX512_F
+code path, and generic gradients against its select/xor code path (tests/conftest.py FLAVOURS).
 """
 import os
 
@@ -25,8 +27,8 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def test_golden_vectors_bit_exact(gpu):
-    outputs, summary, _ = helpers.load_golden()
+def test_golden_vectors_bit_exact(gpu, flavour):
+    outputs, summary, _ = helpers.load_golden(flavour.golden)
     before = gpu.lib.fnb200LaunchCount()
     for name, case in cases.GOLDEN_CASES.items():
         out, mm = cases.run_case(helpers.ProductNode(gpu, case["tree"]), case)
@@ -289,12 +291,12 @@ def test_full_size_terrain_slabs_and_range(gpu):
     assert float(whole.min()) == mm_whole[0] and float(whole.max()) == mm_whole[1]
 
 
-def test_relaxed_math_mode_within_tolerance(gpu, ref):
+def test_relaxed_math_mode_within_tolerance(gpu, ref, flavour):
     """FMA contraction + approximate rsqrt/rcp: >= 95 % of points within 2e-5 of the strict oracle and every point within
     5e-3 (a contracted skew can flip a simplex lattice decision on ~0.2 % of points, |d| up to 1.7e-3 -- the same band the
     reference's own relaxed CPU builds show against its strict build, tests/test_oracle.py). C3b is excluded: White hashes
     coordinate BIT PATTERNS, so it is only meaningful in strict mode."""
-    gpu.set_math_mode(1)
+    gpu.set_math_mode(flavour.mode | 1)
     try:
         for name in ("c1_simplex", "c3a_cellular_distance", "c3c_cellular_lookup_gradient", "c4_terrain"):
             tree = gpu.TREES[name]
@@ -305,7 +307,7 @@ def test_relaxed_math_mode_within_tolerance(gpu, ref):
             assert (d <= TOL).mean() >= 0.95, (name, float((d <= TOL).mean()))
             assert d.max() <= 5e-3 or name == "c3c_cellular_lookup_gradient", (name, float(d.max()))
     finally:
-        gpu.set_math_mode(0)
+        gpu.set_math_mode(flavour.mode)
 
 
 def test_philox_fill_is_reproducible_and_uniform(gpu):

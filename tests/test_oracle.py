@@ -5,8 +5,8 @@ import pytest
 from tests import cases, helpers
 
 
-def test_strict_ref_reproduces_golden_vectors(ref):
-    outputs, summary, _ = helpers.load_golden()
+def test_strict_ref_reproduces_golden_vectors(ref, flavour):
+    outputs, summary, _ = helpers.load_golden(flavour.golden)
     for name, case in cases.GOLDEN_CASES.items():
         out, mm = cases.run_case(helpers.RefNode(ref, case["tree"]), case)
         assert np.array_equal(out.view(np.uint32), outputs[name].view(np.uint32)), name
@@ -14,8 +14,10 @@ def test_strict_ref_reproduces_golden_vectors(ref):
         assert float(mm[0]) == summary[name]["min"] and float(mm[1]) == summary[name]["max"]
 
 
-def test_strict_ref_reproduces_survey_checksums(ref, fn):
+def test_strict_ref_reproduces_survey_checksums(ref, fn, flavour):
     """An independent build of the same semantics (the survey's scalar prototype) produced these FNV-1a values."""
+    if flavour.name != "generic":
+        pytest.skip("the survey's prototype followed the generic gradient code path")
     trees = {**fn.TREES, **cases.DEMO_TREES}
     for name, (kind, fnv, lo, hi) in cases.SURVEY_SMOKE.items():
         out, mm = cases.run_case(helpers.RefNode(ref, trees[name]), dict(cases.survey_call(kind), tree=trees[name]))
@@ -23,10 +25,10 @@ def test_strict_ref_reproduces_survey_checksums(ref, fn):
         assert abs(float(mm[0]) - lo) < 2e-6 and abs(float(mm[1]) - hi) < 2e-6, name
 
 
-def test_relaxed_ref_stays_inside_the_tolerance_band(ref, fn):
+def test_relaxed_ref_stays_inside_the_tolerance_band(ref, fn, flavour):
     """The timing build (reference default flags: -ffast-math, rsqrt/rcp approximations) differs from the strict one only
     in low bits on smooth nodes -- the band real reference binaries occupy among themselves."""
-    relaxed = helpers.load_ref("relaxed_avx2")
+    relaxed = helpers.load_ref("relaxed_avx512" if flavour.name == "tables" else "relaxed_avx2")
     if relaxed is None:
         pytest.skip("relaxed build missing")
     # measured here (AVX2 / AVX-512 relaxed vs strict): smooth trees agree to 4e-6; Simplex flips a lattice decision on 0.2 %
@@ -41,12 +43,9 @@ def test_relaxed_ref_stays_inside_the_tolerance_band(ref, fn):
         assert (d <= 2e-5).mean() >= frac and d.max() <= worst, (name, float((d <= 2e-5).mean()), float(d.max()))
 
 
-def test_port_oracle_reproduces_golden_vectors():
+def test_port_oracle_reproduces_golden_vectors(port, flavour):
     """oracle/fn2_oracle.c (plain C restatement) against the committed vectors; runs with or without /root/reference."""
-    port = helpers.load_port()
-    if port is None:
-        pytest.skip("oracle/libfn2oracle.so not built (make -C oracle port)")
-    outputs, summary, _ = helpers.load_golden()
+    outputs, summary, _ = helpers.load_golden(flavour.golden)
     checked = 0
     for name, case in cases.GOLDEN_CASES.items():
         node = helpers.PortNode(port, case["tree"])
@@ -72,12 +71,9 @@ def test_test_encoder_matches_known_strings(fn):
     assert c4.encode() == fn.TREES["c4_terrain"]
 
 
-def test_port_oracle_vs_strict_ref_every_node(ref):
+def test_port_oracle_vs_strict_ref_every_node(ref, port):
     """The C restatement against the reference's own sources, every node type it covers, 2D/3D/4D, constant and generated hybrids."""
     from tests.encode import default_tree
-    port = helpers.load_port()
-    if port is None:
-        pytest.skip("oracle/libfn2oracle.so not built")
     checked = 0
     for hybrid_nodes in (False, True):
         for node_id in list(range(47)) + [16, 17]:  # second visit of the simplex warps: GradientOuterProduct scheme
@@ -96,10 +92,7 @@ def test_port_oracle_vs_strict_ref_every_node(ref):
     assert checked == 49 * 2 * 3
 
 
-def test_port_oracle_slab_rows_equal_whole_grid():
-    port = helpers.load_port()
-    if port is None:
-        pytest.skip("oracle/libfn2oracle.so not built")
+def test_port_oracle_slab_rows_equal_whole_grid(port):
     from fastnoise2_b200.api import TREES
     node = helpers.PortNode(port, TREES["c4_terrain"])
     whole, mm = node.grid3d(0.0, 0.0, 0.0, 12, 10, 9, 3.3, 3.3, 3.3, 1337)
