@@ -21,11 +21,11 @@ namespace fn2
         {
             i32 h = hash_hb( seed, x0, y0 );
             float c = xs0 * ys0;
-            xWarp = c * cvt_f( h & 0xffff );
+            xWarp = c * field_f<0, 16>( h );
             yWarp = c * cvt_f( lsr( h, 16 ) );
         }
 #define FN2_CORNER( XS, YS, XP, YP ) { i32 h = hash_hb( seed, XP, YP ); float c = XS * YS; \
-            xWarp = fma_( c, cvt_f( h & 0xffff ), xWarp ); yWarp = fma_( c, cvt_f( lsr( h, 16 ) ), yWarp ); }
+            xWarp = fma_( c, field_f<0, 16>( h ), xWarp ); yWarp = fma_( c, cvt_f( lsr( h, 16 ) ), yWarp ); }
         FN2_CORNER( xs1, ys0, x1, y0 )
         FN2_CORNER( xs0, ys1, x0, y1 )
         FN2_CORNER( xs1, ys1, x1, y1 )
@@ -51,12 +51,12 @@ namespace fn2
         {
             i32 h = hash_hb( seed, x0, y0, z0 );
             float c = xs0 * ys0 * zs0;
-            xWarp = c * cvt_f( h & 0x3ff );
-            yWarp = c * cvt_f( ( h >> 11 ) & 0x3ff );
+            xWarp = c * field_f<0, 10>( h );
+            yWarp = c * field_f<11, 10>( h );
             zWarp = c * cvt_f( lsr( h, 22 ) );
         }
 #define FN2_CORNER( XS, YS, ZS, XP, YP, ZP ) { i32 h = hash_hb( seed, XP, YP, ZP ); float c = XS * YS * ZS; \
-            xWarp = fma_( c, cvt_f( h & 0x3ff ), xWarp ); yWarp = fma_( c, cvt_f( ( h >> 11 ) & 0x3ff ), yWarp ); zWarp = fma_( c, cvt_f( lsr( h, 22 ) ), zWarp ); }
+            xWarp = fma_( c, field_f<0, 10>( h ), xWarp ); yWarp = fma_( c, field_f<11, 10>( h ), yWarp ); zWarp = fma_( c, cvt_f( lsr( h, 22 ) ), zWarp ); }
         FN2_CORNER( xs1, ys0, zs0, x1, y0, z0 )
         FN2_CORNER( xs0, ys1, zs0, x0, y1, z0 )
         FN2_CORNER( xs1, ys1, zs0, x1, y1, z0 )
@@ -89,13 +89,13 @@ namespace fn2
         {
             i32 h = hash_hb( seed, x0, y0, z0, w0 );
             float c = xs0 * ys0 * zs0 * ws0;
-            xWarp = c * cvt_f( h & 0xff );
-            yWarp = c * cvt_f( ( h >> 8 ) & 0xff );
+            xWarp = c * field_f<0, 8>( h );
+            yWarp = c * field_f<8, 8>( h );
             zWarp = c * cvt_f( ( h >> 16 ) & 0xff );
             wWarp = c * cvt_f( lsr( h, 24 ) );
         }
 #define FN2_CORNER( XS, YS, ZS, WS, XP, YP, ZP, WP ) { i32 h = hash_hb( seed, XP, YP, ZP, WP ); float c = XS * YS * ZS * WS; \
-            xWarp = fma_( c, cvt_f( h & 0xff ), xWarp ); yWarp = fma_( c, cvt_f( ( h >> 8 ) & 0xff ), yWarp ); \
+            xWarp = fma_( c, field_f<0, 8>( h ), xWarp ); yWarp = fma_( c, field_f<8, 8>( h ), yWarp ); \
             zWarp = fma_( c, cvt_f( ( h >> 16 ) & 0xff ), zWarp ); wWarp = fma_( c, cvt_f( lsr( h, 24 ) ), wWarp ); }
         FN2_CORNER( xs1, ys0, zs0, ws0, x1, y0, z0, w0 )
         FN2_CORNER( xs0, ys1, zs0, ws0, x0, y1, z0, w0 )

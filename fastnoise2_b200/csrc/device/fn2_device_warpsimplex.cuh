@@ -27,11 +27,11 @@ namespace fn2
         i32 indexOuter = imul( hashShifted, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;          // [0,12) in bits 0,1,30,31
 #if FN2_TABLES
         // [:13-25]
-        const float* g = sGradientTables + kTabGop2 + ( ( indexGradient >> 28 ) & 15 );
-        const float* o = sGradientTables + kTabGop2 + ( ( indexOuter | ( indexOuter >> 28 ) ) & 15 );
-        multiplier *= fma_( fY, g[16], fX * g[0] );
-        valueX = fma_( multiplier, o[0], valueX );
-        valueY = fma_( multiplier, o[16], valueY );
+        const float2 g = table_pair( kTabGop2, ( ( indexGradient >> 28 ) & 15 ) * 2 );
+        const float2 o = table_pair( kTabGop2, ( ( indexOuter | ( indexOuter >> 28 ) ) & 15 ) * 2 );
+        multiplier *= fma_( fY, g.y, fX * g.x );
+        valueX = fma_( multiplier, o.x, valueX );
+        valueY = fma_( multiplier, o.y, valueY );
         return;
 #endif
         {
@@ -59,12 +59,13 @@ namespace fn2
         indexOuter |= indexOuter >> 28;
 #if FN2_TABLES
         // [:70-81] the 12 directions are the first 12 entries of the common 3D gradient table
-        const float* g = sGradientTables + kTabCommon3 + indexGradient;
-        const float* o = sGradientTables + kTabCommon3 + ( indexOuter & 15 );
-        multiplier *= fma_( g[32], fZ, fma_( fY, g[16], fX * g[0] ) );
-        valueX = fma_( multiplier, o[0], valueX );
-        valueY = fma_( multiplier, o[16], valueY );
-        valueZ = fma_( multiplier, o[32], valueZ );
+        const int slotG = indexGradient * 2, slotO = ( indexOuter & 15 ) * 2;
+        const float2 g = table_pair( kTabCommon3XY, slotG );
+        const float2 o = table_pair( kTabCommon3XY, slotO );
+        multiplier *= fma_( sGradientTables[kTabCommon3Z + slotG], fZ, fma_( fY, g.y, fX * g.x ) );
+        valueX = fma_( multiplier, o.x, valueX );
+        valueY = fma_( multiplier, o.y, valueY );
+        valueZ = fma_( multiplier, sGradientTables[kTabCommon3Z + slotO], valueZ );
         return;
 #endif
         {
