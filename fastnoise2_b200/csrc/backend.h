@@ -50,6 +50,7 @@ namespace FastNoise
         };
 
         const std::string& LastError();
+        long long SelfTestInvSqrt( float lo, float hi ); // device_check.cu
         int MathMode();
         void SetMathMode( int mode );
         unsigned long long LaunchCount();

@@ -376,4 +376,5 @@ extern "C"
     }
 
     double fnb200MeasureAluPeak( int mode, int iters ) { return Impl::MeasureAluPeak( mode, iters ); }
+    long long fnb200SelfTestInvSqrt( float lo, float hi ) { return Impl::SelfTestInvSqrt( lo, hi ); }
 }

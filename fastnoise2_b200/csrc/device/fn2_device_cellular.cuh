@@ -29,7 +29,7 @@ namespace fn2
     {
         xd = cvt_f( hash & 0x7ff ) - ( 0x7ff / 2.0f );
         yd = cvt_f( lsr( hash, 21 ) ) - ( 0x7ff / 2.0f );
-        return jitter * inv_sqrt( fma_( xd, xd, yd * yd ) );
+        return jitter * inv_sqrt_bounded( fma_( xd, xd, yd * yd ) );
     }
     // [Cellular.inl:148-152] 3D: three 10-bit fields at bits 0, 11, 22
     FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd )
@@ -37,7 +37,7 @@ namespace fn2
         xd = cvt_f( hash & 0x3ff ) - ( 0x3ff / 2.0f );
         yd = cvt_f( ( hash >> 11 ) & 0x3ff ) - ( 0x3ff / 2.0f );
         zd = cvt_f( lsr( hash, 22 ) ) - ( 0x3ff / 2.0f );
-        return jitter * inv_sqrt( fma_( xd, xd, fma_( yd, yd, zd * zd ) ) );
+        return jitter * inv_sqrt_bounded( fma_( xd, xd, fma_( yd, yd, zd * zd ) ) );
     }
     // [Cellular.inl:247-252] 4D: four bytes
     FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd, float& wd )
@@ -46,7 +46,7 @@ namespace fn2
         yd = cvt_f( ( hash >> 8 ) & 0xff ) - ( 0xff / 2.0f );
         zd = cvt_f( ( hash >> 16 ) & 0xff ) - ( 0xff / 2.0f );
         wd = cvt_f( lsr( hash, 24 ) ) - ( 0xff / 2.0f );
-        return jitter * inv_sqrt( fma_( xd, xd, fma_( yd, yd, fma_( zd, zd, wd * wd ) ) ) );
+        return jitter * inv_sqrt_bounded( fma_( xd, xd, fma_( yd, yd, fma_( zd, zd, wd * wd ) ) ) );
     }
 
     // per-cell distance multiplier of the size jitter [Cellular.inl:66-70, 160-164, 260-264]

@@ -3,6 +3,8 @@
 // nvcc compile the same text for sm_100a at build time (syntax, -Xptxas -v register counts, cuobjdump -sass)
 // and provides one fixed kernel per leaf so the library can be smoke-tested without NVRTC.
 #define FN2_RELAXED 0
+#include <cstring>
+#include <cuda_runtime.h>
 #include "fn2_device.cuh"
 
 namespace
@@ -54,4 +56,40 @@ extern "C" __global__ void __launch_bounds__( 256 ) fn2_device_check( float* __r
     case 23: v = fn2::sinewave( x, y, z, w ) + fn2::checkerboard( x, y, z ) + fn2::pow_pos( fn2::abs_( x ) + 0.5f, 1.5f ) + fn2::modulus( x, 3.0f ); break;
     }
     out[i] = v;
+}
+
+// Exhaustive equality of the check-free Newton sequence with the IEEE intrinsics over a range of float bit patterns.
+extern "C" __global__ void __launch_bounds__( 256 ) fn2_selftest_inv_sqrt( unsigned firstBits, unsigned count, unsigned long long* __restrict__ mismatches )
+{
+    const unsigned stride = gridDim.x * 256u;
+    unsigned long long bad = 0;
+    for( unsigned i = blockIdx.x * 256u + threadIdx.x; i < count; i += stride )
+    {
+        const float v = __int_as_float( (int)( firstBits + i ) );
+        bad += __float_as_int( fn2::inv_sqrt_bounded( v ) ) != __float_as_int( fn2::inv_sqrt( v ) );
+    }
+    if( bad ) atomicAdd( mismatches, bad );
+}
+
+namespace FastNoise
+{
+    namespace Impl
+    {
+        // 0 = every value agrees; > 0 = mismatch count; < 0 = CUDA error
+        long long SelfTestInvSqrt( float lo, float hi )
+        {
+            unsigned a, b;
+            memcpy( &a, &lo, 4 );
+            memcpy( &b, &hi, 4 );
+            if( !( lo > 0.0f ) || b <= a ) return -1;
+            unsigned long long* counter = nullptr;
+            if( cudaMalloc( &counter, 8 ) != cudaSuccess ) return -2;
+            cudaMemset( counter, 0, 8 );
+            fn2_selftest_inv_sqrt<<<148 * 8, 256>>>( a, b - a, counter );
+            unsigned long long result = 0;
+            const cudaError_t e = cudaMemcpy( &result, counter, 8, cudaMemcpyDeviceToHost );
+            cudaFree( counter );
+            return e == cudaSuccess ? (long long)result : -3;
+        }
+    }
 }

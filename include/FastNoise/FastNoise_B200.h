@@ -87,6 +87,10 @@ FASTNOISE_API int fnb200FillUniformPhilox( float* deviceOut, long long count, lo
  * FFMA+LOP3 mix (mode 3) on every SM and returns achieved lane-ops per second (0 on failure). */
 FASTNOISE_API double fnb200MeasureAluPeak( int mode, int iters );
 
+/* Self-test: compares the check-free inverse square root the Cellular nodes use (valid on [0.5, 2^23)) with the IEEE
+ * 1/sqrt sequence for EVERY float in [lo, hi). Returns the number of differing values (0 = identical), < 0 on a CUDA error. */
+FASTNOISE_API long long fnb200SelfTestInvSqrt( float lo, float hi );
+
 /* Decodes `encodedString` into NodeData records (Metadata::DeserialiseNodeData) and serialises them again
  * (Metadata::SerialiseNodeData): the canonical spelling of a tree. Writes a NUL-terminated string into buf
  * (truncated to bufSize) and returns its full length, 0 if the input does not decode. */

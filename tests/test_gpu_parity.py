@@ -320,3 +320,10 @@ def test_philox_fill_is_reproducible_and_uniform(gpu):
     torch.cuda.synchronize()
     assert torch.equal(a[1 << 19:], b)  # counter-based: any rank regenerates any index range
     assert -1000.0 <= float(a.min()) and float(a.max()) < 1000.0 and abs(float(a.mean())) < 3.0
+
+
+def test_bounded_inv_sqrt_equals_ieee_on_its_whole_domain(gpu):
+    """The Cellular jitter vectors use a check-free Newton sequence for 1/sqrt (fn2::inv_sqrt_bounded). Its arguments are sums
+    of squares of half-odd integers, all inside [0.5, 2^22); every one of the 193 M floats of [0.5, 2^23) must give the bits
+    of the IEEE `1 / sqrt` sequence the strict oracle computes."""
+    assert gpu.lib.fnb200SelfTestInvSqrt(0.5, float(2 ** 23)) == 0
