@@ -35,7 +35,7 @@ namespace fn2
     FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd )
     {
         xd = cvt_f( hash & 0x3ff ) - ( 0x3ff / 2.0f );
-        yd = cvt_f( ( hash >> 11 ) & 0x3ff ) - ( 0x3ff / 2.0f );
+        yd = field_minus<11, 10>( hash, 0x3ff / 2.0f );
         zd = cvt_f( lsr( hash, 22 ) ) - ( 0x3ff / 2.0f );
         return jitter * inv_sqrt_bounded( fma_( xd, xd, fma_( yd, yd, zd * zd ) ) );
     }
@@ -43,14 +43,14 @@ namespace fn2
     FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd, float& wd )
     {
         xd = cvt_f( hash & 0xff ) - ( 0xff / 2.0f );
-        yd = cvt_f( ( hash >> 8 ) & 0xff ) - ( 0xff / 2.0f );
+        yd = field_minus<8, 8>( hash, 0xff / 2.0f );
         zd = cvt_f( ( hash >> 16 ) & 0xff ) - ( 0xff / 2.0f );
         wd = cvt_f( lsr( hash, 24 ) ) - ( 0xff / 2.0f );
         return jitter * inv_sqrt_bounded( fma_( xd, xd, fma_( yd, yd, fma_( zd, zd, wd * wd ) ) ) );
     }
 
     // per-cell distance multiplier of the size jitter [Cellular.inl:66-70, 160-164, 260-264]
-    FN2_DI float size_jitter2( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( ( hash >> 11 ) & 0x3ff ), 1.0f ); }
+    FN2_DI float size_jitter2( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, field_f<11, 10>( hash ), 1.0f ); }
     FN2_DI float size_jitter3( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xffff ), 1.0f ); }
     FN2_DI float size_jitter4( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xfffff ), 1.0f ); }
 
