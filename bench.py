@@ -360,12 +360,17 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    traffic = None
-    try:  # DRAM bytes per launch of this workload's kernel from the committed `ncu --set full` capture (never measured under a timer)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+    # From the committed `ncu --set full` capture of this workload's kernel (never measured under a timer here): DRAM bytes per
+    # launch and the thread-instructions the kernel executes per point -- the work this implementation actually issues.
+    traffic, inst_per_point = None, None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json"))).get(args.workload, {})
+        traffic = prof.get("dram_bytes_per_launch")
+        inst_per_point = prof.get("thread_inst_per_point") if args.math == "strict" else None
     except (OSError, ValueError):
         pass
-    achieved = w["ops"] * points / (kernel_ms * 1e-3) / 1e12
+    ref_ops = w["ops"] * points / (kernel_ms * 1e-3) / 1e12
+    achieved = (inst_per_point if inst_per_point else w["ops"]) * points / (kernel_ms * 1e-3) / 1e12
     peak = alu_peak / 1e12
     store_gbs = out_bytes / (kernel_ms * 1e-3) / 1e9
     line = {
@@ -377,10 +382,14 @@ def main():
                    "points_per_gpu": points, "sharding": "z-slab (outermost axis) per rank, global integer indices" if world > 1 else "none",
                    "math": args.math, "l2": "output per step (%d MiB) exceeds L2; no inputs are re-read" % (out_bytes >> 20),
                    "output_minmax": [lo, hi]},
-        "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak if peak else None,
+        "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-inst/s", "frac": achieved / peak if peak else None,
+                     "achieved_is": ("thread-instructions issued per second = %.1f inst/point (profiles/r1_ncu_summary.json, ncu) x points / kernel time" % inst_per_point) if inst_per_point
+                     else "reference lane-ops per second (SURVEY 8d ops/point x points / kernel time); no ncu instruction count committed for this workload+mode",
                      "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)" if traffic else None,
                      "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-specialised tree kernel)", "kernel_ms": kernel_ms,
-                     "ops_per_point": w["ops"], "peak_source": "FFMA issue rate measured live by fnb200MeasureAluPeak (148 SM x 128 lanes x clock); MEASURED_PEAKS.json has no ALU entry",
+                     "inst_per_point": inst_per_point,
+                     "reference_ops": {"ops_per_point": w["ops"], "tlane_ops_per_s": ref_ops, "note": "SURVEY 8d count of the reference's generic-path SIMD lane-ops; the GPU needs fewer instructions"},
+                     "peak_source": "FFMA issue rate measured live by fnb200MeasureAluPeak (148 SM x 128 lanes x clock = the SM issue limit); MEASURED_PEAKS.json has no ALU entry",
                      "hbm_store": {"achieved_gbs": store_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": store_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                    "algorithmic_bytes_per_point": 4 + (16 if kind == "pos4d" else 0)}},
         "cpu_baseline": cpu,

@@ -41,20 +41,29 @@ def main():
     tag = sys.argv[1]
     here = os.path.dirname(os.path.abspath(__file__))
     summary = {}
+    sys.path.insert(0, os.path.dirname(here))
+    import bench
     for arg in sys.argv[2:]:
         path, workload = arg.rsplit(":", 1)
         summary[workload] = read_report(path)
-        summary[workload]["dram_bytes_per_launch"] = summary[workload].get("dram__bytes_read.sum", 0) + summary[workload].get("dram__bytes_write.sum", 0)
+        m = summary[workload]
+        m["dram_bytes_per_launch"] = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+        points = 1
+        for n in bench.WORKLOADS[workload]["n"]:
+            points *= n
+        m["points_per_launch"] = points
+        m["thread_inst_per_point"] = m["smsp__inst_executed.sum"] * m["smsp__thread_inst_executed_per_inst_executed.ratio"] / points
     json.dump(summary, open(os.path.join(here, "%s_ncu_summary.json" % tag), "w"), indent=1)
     lines = ["# ncu --set full --clock-control none, kernel fn2_entry (one launch per workload), round %s" % tag, "",
-             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | tensor % | warp-inst | DRAM read | DRAM write | local ld/st |",
-             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | lsu pipe % | tensor % | thread-inst/point | DRAM read | DRAM write | local ld/st |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for w, m in summary.items():
-        lines.append("| %s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.3g | %.3g B | %.3g B | %d/%d |" % (
+        lines.append("| %s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.3g B | %.3g B | %d/%d |" % (
             w, m["gpu__time_duration.sum"] * 1e3, m["launch__registers_per_thread"], m["sm__warps_active.avg.pct_of_peak_sustained_active"],
             m["smsp__issue_active.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
             m["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"],
-            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["smsp__inst_executed.sum"], m.get("dram__bytes_read.sum", 0),
+            m.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", 0),
+            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["thread_inst_per_point"], m.get("dram__bytes_read.sum", 0),
             m.get("dram__bytes_write.sum", 0), m.get("sass__inst_executed_local_loads", 0), m.get("sass__inst_executed_local_stores", 0)))
     open(os.path.join(here, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
