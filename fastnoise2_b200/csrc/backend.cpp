@@ -453,7 +453,7 @@ namespace FastNoise
         static int MaxPointsPerThread()
         {
             int p = EnvInt( "FASTNOISE2_B200_PPT", 4 );
-            return p >= 4 ? 4 : ( p >= 2 ? 2 : 1 );
+            return p >= 8 ? 8 : ( p >= 4 ? 4 : ( p >= 2 ? 2 : 1 ) );
         }
 
         // --------------------------------------------------------------- launches (device pointers)
@@ -530,7 +530,7 @@ namespace FastNoise
                              const float offset[4], int seed, unsigned* deviceMinMax, cudaStream_t stream )
         {
             if( count == 0 ) return 0;
-            const int ppt = MaxPointsPerThread();
+            const int ppt = MaxPointsPerThread() > 4 ? 4 : MaxPointsPerThread();
             const Module* m = nullptr;
             if( int rc = ModuleFor( root, 10 + dims, ppt, m ) ) return rc;
 

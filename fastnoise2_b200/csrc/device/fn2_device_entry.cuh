@@ -87,7 +87,12 @@ namespace fn2
     template<int P>
     FN2_DI void store_points( float* __restrict__ out, u32 first, const float ( &v )[P], bool vec )
     {
-        if( P == 4 && vec )
+        if( P == 8 && vec )
+        {
+            *reinterpret_cast<float4*>( out + first ) = make_float4( v[0], v[1], v[2], v[3] );
+            *reinterpret_cast<float4*>( out + first + 4 ) = make_float4( v[P > 4 ? 4 : 0], v[P > 5 ? 5 : 0], v[P > 6 ? 6 : 0], v[P > 7 ? 7 : 0] );
+        }
+        else if( P == 4 && vec )
         {
             *reinterpret_cast<float4*>( out + first ) = make_float4( v[0], v[1], v[2], v[3] );
         }

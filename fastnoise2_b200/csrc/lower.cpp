@@ -823,7 +823,7 @@ namespace FastNoise
         {
             LoweredProgram program;
             program.pointsPerThread = pointsPerThread;
-            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 2 && pointsPerThread != 4 ) )
+            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 2 && pointsPerThread != 4 && pointsPerThread != 8 ) )
             {
                 program.error = "invalid lowering request";
                 return program;

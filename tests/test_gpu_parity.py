@@ -327,3 +327,29 @@ def test_bounded_inv_sqrt_equals_ieee_on_its_whole_domain(gpu):
     of squares of half-odd integers, all inside [0.5, 2^22); every one of the 193 M floats of [0.5, 2^23) must give the bits
     of the IEEE `1 / sqrt` sequence the strict oracle computes."""
     assert gpu.lib.fnb200SelfTestInvSqrt(0.5, float(2 ** 23)) == 0
+
+
+def test_lattice_aligned_grids(gpu, ref):
+    """Integer coordinates at feature scale 1 put every point on a lattice vertex: offsets and gradient dots are exact zeros
+    (whose sign is one of the places the two gradient flavours differ: a zero table weight contributes a signed zero) and
+    every floor / round-to-nearest decision sits on a tie. Bits must still match the flavour's own reference build."""
+    def build(lib, node_id):
+        t = trees.Tree(lib)
+        h = t.new(node_id)
+        t.set_float(h, "Feature Scale", 1.0)
+        return t, h
+    for node_id in (6, 7, 8, 9, 10, 11):            # Simplex, SuperSimplex, Perlin, Value, CellularValue, CellularDistance
+        for dim, n in ((2, 24), (3, 12), (4, 6)):
+            outs = []
+            for lib in (gpu.lib, ref):
+                t, h = build(lib, node_id)
+                out = np.empty(n ** dim, np.float32)
+                if dim == 2:
+                    lib.fnGenUniformGrid2D(h, out.ctypes.data, -7.0, -5.0, n, n, 1.0, 1.0, 1337, None)
+                elif dim == 3:
+                    lib.fnGenUniformGrid3D(h, out.ctypes.data, -7.0, -5.0, -3.0, n, n, n, 1.0, 1.0, 1.0, 1337, None)
+                else:
+                    lib.fnGenUniformGrid4D(h, out.ctypes.data, -3.0, -2.0, -1.0, 0.0, n, n, n, n, 1.0, 1.0, 1.0, 1.0, 1337, None)
+                outs.append(out)
+                t.close()
+            assert np.array_equal(bits(outs[0]), bits(outs[1])), (node_id, dim, helpers.compare(outs[0], outs[1]))
