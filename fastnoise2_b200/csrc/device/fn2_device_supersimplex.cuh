@@ -38,10 +38,10 @@ namespace fn2
         float dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
 
         float falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
-        v[0] = { hash_primes( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
+        v[0] = { hash_hb( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
         { // vertex <1,1>
             float falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
-            v[1] = { hash_primes( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
+            v[1] = { hash_hb( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
         }
 
         float xyDelta = forwardXY ? (float)( kUnskew2 + 1 ) : (float)( -kUnskew2 );
@@ -55,7 +55,7 @@ namespace fn2
             float dx = dxBase - ( forwardX ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
             float dy = forwardX ? dyBase - (float)( 2 * kUnskew2 ) : dyBase;
             float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            v[2] = { hash_primes( seed, xv, yv ), dx, dy, pow4( falloff ) };
+            v[2] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
         { // vertex <0,1> or <0,-1> or <2,1>
             i32 xv = forwardXY ? iadd( xP, kPX ) : xP;
@@ -64,7 +64,7 @@ namespace fn2
             float dx = forwardY ? dxBase - (float)( 2 * kUnskew2 ) : dxBase;
             float dy = dyBase - ( forwardY ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
             float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            v[3] = { hash_primes( seed, xv, yv ), dx, dy, pow4( falloff ) };
+            v[3] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
     }
 
@@ -72,9 +72,9 @@ namespace fn2
     {
         Verts2 v[4];
         supersimplex2_vertices( seed, x, y, v );
-        float value = v[0].falloff * grad_dot2( v[0].hash, v[0].dx, v[0].dy );
+        float value = v[0].falloff * grad_dot2( v[0].hb, v[0].dx, v[0].dy );
 #pragma unroll
-        for( int k = 1; k < 4; k++ ) value = fma_( v[k].falloff, grad_dot2( v[k].hash, v[k].dx, v[k].dy ), value );
+        for( int k = 1; k < 4; k++ ) value = fma_( v[k].falloff, grad_dot2( v[k].hb, v[k].dx, v[k].dy ), value );
         return value;
     }
 
@@ -135,56 +135,56 @@ namespace fn2
             float fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            v[0] = { hash_primes( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
+            v[0] = { hash_hb( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
         }
         { // <1,1,1> or <-1,-1,-1>
             bool sm = xyzN < 0.0f;
             i32 sign = signbit_if( sm );
             float o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
             float fb = max_( fma_( o, coordSum, stemA ), 0.0f );
-            v[1] = { hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
+            v[1] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
         }
         { // <1,1,0> or <-1,-1,0>
             bool sm = xyzN < zN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             float fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
-            v[2] = { hash_primes( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
+            v[2] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
         }
         { // <1,0,1> or <-1,0,-1>
             bool sm = xyzN < yN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             float fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
-            v[3] = { hash_primes( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
+            v[3] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
         }
         { // <0,1,1> or <0,-1,-1>
             bool sm = xyzN < xN;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             float fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
-            v[4] = { hash_primes( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
+            v[4] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
         }
         { // <1,0,0> or <-1,0,0>
             bool sm = xN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
-            v[5] = { hash_primes( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
+            v[5] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
         }
         { // <0,1,0> or <0,-1,0>
             bool sm = yN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
-            v[6] = { hash_primes( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
+            v[6] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
         }
         { // <0,0,1> or <0,0,-1>
             bool sm = zN < 0.0f;
             i32 sign = signbit_if( sm );
             float o0 = fxor( (float)kReflectUnskew3, sign );
             float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
-            v[7] = { hash_primes( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
+            v[7] = { hash_hb( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
         }
     }
 
@@ -192,9 +192,9 @@ namespace fn2
     {
         Verts3 v[8];
         supersimplex3_vertices( seed, x, y, z, v );
-        float value = v[0].falloff * grad_dot3( v[0].hash, v[0].dx, v[0].dy, v[0].dz );
+        float value = v[0].falloff * grad_dot3( v[0].hb, v[0].dx, v[0].dy, v[0].dz );
 #pragma unroll
-        for( int k = 1; k < 8; k++ ) value = fma_( v[k].falloff, grad_dot3( v[k].hash, v[k].dx, v[k].dy, v[k].dz ), value );
+        for( int k = 1; k < 8; k++ ) value = fma_( v[k].falloff, grad_dot3( v[k].hb, v[k].dx, v[k].dy, v[k].dz ), value );
         return value;
     }
 
@@ -268,7 +268,7 @@ namespace fn2
             float fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            v[0] = { hash_primes( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
+            v[0] = { hash_hb( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
         }
 
         // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many.
@@ -282,7 +282,7 @@ namespace fn2
             float o0 = fxor( (float)( K * kUnskew4 ), sign ); \
             (void)o0; \
             float fb = max_( FALLOFF, 0.0f ); \
-            v[SLOT] = { hash_primes( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
+            v[SLOT] = { hash_hb( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
                                      MZ ? step_prime( zP, kPZ, sm ) : zP, MW ? step_prime( wP, kPW, sm ) : wP ), \
                         dxB - ( MX ? o1 : o0 ), dyB - ( MY ? o1 : o0 ), dzB - ( MZ ? o1 : o0 ), dwB - ( MW ? o1 : o0 ), sq2( fb ) }; \
         }
@@ -309,9 +309,9 @@ namespace fn2
     {
         Verts4 v[16];
         supersimplex4_vertices( seed, x, y, z, w, v );
-        float value = v[0].falloff * grad_dot4( v[0].hash, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
+        float value = v[0].falloff * grad_dot4( v[0].hb, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
 #pragma unroll
-        for( int k = 1; k < 16; k++ ) value = fma_( v[k].falloff, grad_dot4( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].dw ), value );
+        for( int k = 1; k < 16; k++ ) value = fma_( v[k].falloff, grad_dot4( v[k].hb, v[k].dx, v[k].dy, v[k].dz, v[k].dw ), value );
         return value;
     }
 }

@@ -27,8 +27,8 @@ namespace fn2
         i32 indexOuter = imul( hashShifted, (i32)0xAAAAAAABu ) & (i32)0xC0000003u;          // [0,12) in bits 0,1,30,31
 #if FN2_TABLES
         // [:13-25]
-        const float2 g = table_pair( kTabGop2, ( ( indexGradient >> 28 ) & 15 ) * 2 );
-        const float2 o = table_pair( kTabGop2, ( ( indexOuter | ( indexOuter >> 28 ) ) & 15 ) * 2 );
+        const float2 g = table_pair( kTabGop2, ( ( indexGradient >> 28 ) & 15 ) * 8 );
+        const float2 o = table_pair( kTabGop2, ( ( indexOuter | ( indexOuter >> 28 ) ) & 15 ) * 8 );
         multiplier *= fma_( fY, g.y, fX * g.x );
         valueX = fma_( multiplier, o.x, valueX );
         valueY = fma_( multiplier, o.y, valueY );
@@ -59,13 +59,13 @@ namespace fn2
         indexOuter |= indexOuter >> 28;
 #if FN2_TABLES
         // [:70-81] the 12 directions are the first 12 entries of the common 3D gradient table
-        const int slotG = indexGradient * 2, slotO = ( indexOuter & 15 ) * 2;
+        const int slotG = indexGradient * 8, slotO = ( indexOuter & 15 ) * 8;
         const float2 g = table_pair( kTabCommon3XY, slotG );
         const float2 o = table_pair( kTabCommon3XY, slotO );
-        multiplier *= fma_( sGradientTables[kTabCommon3Z + slotG], fZ, fma_( fY, g.y, fX * g.x ) );
+        multiplier *= fma_( table_first( kTabCommon3Z, slotG ), fZ, fma_( fY, g.y, fX * g.x ) );
         valueX = fma_( multiplier, o.x, valueX );
         valueY = fma_( multiplier, o.y, valueY );
-        valueZ = fma_( multiplier, sGradientTables[kTabCommon3Z + slotO], valueZ );
+        valueZ = fma_( multiplier, table_first( kTabCommon3Z, slotO ), valueZ );
         return;
 #endif
         {
@@ -300,14 +300,14 @@ namespace fn2
             Verts2 v[3];
             simplex2_vertices( seed, x, y, v );
 #pragma unroll
-            for( int k = 0; k < 3; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
+            for( int k = 0; k < 3; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
         }
         else
         {
             Verts2 v[4];
             supersimplex2_vertices( seed, x, y, v );
 #pragma unroll
-            for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
+            for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
         }
         valueX *= boundAx;
         valueY *= boundAy;
@@ -325,14 +325,14 @@ namespace fn2
             Verts3 v[4];
             simplex3_vertices( seed, x, y, z, v );
 #pragma unroll
-            for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
+            for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
         }
         else
         {
             Verts3 v[8];
             supersimplex3_vertices( seed, x, y, z, v );
 #pragma unroll
-            for( int k = 0; k < 8; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
+            for( int k = 0; k < 8; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
         }
         if( SCHEME != 0 ) // match gradient orientation
         {
@@ -361,14 +361,14 @@ namespace fn2
             Verts4 v[5];
             simplex4_vertices( seed, x, y, z, w, v );
 #pragma unroll
-            for( int k = 0; k < 5; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
+            for( int k = 0; k < 5; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
         }
         else
         {
             Verts4 v[16];
             supersimplex4_vertices( seed, x, y, z, w, v );
 #pragma unroll
-            for( int k = 0; k < 16; k++ ) vec_contribution<SCHEME>( v[k].hash, v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
+            for( int k = 0; k < 16; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
         }
         valueX *= boundAx;
         valueY *= boundAy;
