@@ -456,6 +456,26 @@ namespace FastNoise
             return p >= 8 ? 8 : ( p >= 4 ? 4 : ( p >= 2 ? 2 : 1 ) );
         }
 
+        // Threads the current device keeps resident (SM count x 2048): below that a call cannot fill the GPU, so it is worth
+        // trading the instruction-level parallelism of several points per thread for more threads (chunk-sized calls such
+        // as 32^3 are latency-bound: one point per thread finishes ~3x sooner than four).
+        static unsigned long long ResidentThreads()
+        {
+            static const unsigned long long value = []
+            {
+                int device = 0, sms = 148;
+                if( cudaGetDevice( &device ) == cudaSuccess ) cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, device );
+                return (unsigned long long)( sms > 0 ? sms : 148 ) * 2048ull;
+            }();
+            return value;
+        }
+
+        static int PointsPerThreadFor( unsigned long long points, int ppt )
+        {
+            while( ppt > 1 && points / (unsigned)ppt < ResidentThreads() ) ppt >>= 1;
+            return ppt;
+        }
+
         // --------------------------------------------------------------- launches (device pointers)
         static bool Launch( const Module* m, unsigned long long threads, void** args, cudaStream_t stream )
         {
@@ -483,6 +503,7 @@ namespace FastNoise
             }
             int ppt = MaxPointsPerThread();
             while( ppt > 1 && nx % (unsigned)ppt != 0 ) ppt >>= 1;
+            ppt = PointsPerThreadFor( points, ppt );
 
             const Module* m = nullptr;
             if( int rc = ModuleFor( root, call.kind, ppt, m ) ) return rc;
@@ -530,7 +551,7 @@ namespace FastNoise
                              const float offset[4], int seed, unsigned* deviceMinMax, cudaStream_t stream )
         {
             if( count == 0 ) return 0;
-            const int ppt = MaxPointsPerThread() > 4 ? 4 : MaxPointsPerThread();
+            const int ppt = PointsPerThreadFor( count, MaxPointsPerThread() > 4 ? 4 : MaxPointsPerThread() );
             const Module* m = nullptr;
             if( int rc = ModuleFor( root, 10 + dims, ppt, m ) ) return rc;
 
