@@ -353,3 +353,20 @@ def test_lattice_aligned_grids(gpu, ref):
                 outs.append(out)
                 t.close()
             assert np.array_equal(bits(outs[0]), bits(outs[1])), (node_id, dim, helpers.compare(outs[0], outs[1]))
+
+
+def test_random_trees_vs_strict_oracle(gpu, ref):
+    """Fuzz the lowering: random trees over all node types (random parameters, hybrids as generators, dimension changes nested
+    in warps and fractals, shared sub-trees) must reproduce the oracle bit for bit through the C ABI in 2D, 3D and 4D."""
+    from tests.fuzz import TreeFuzzer, same
+    fuzzer = TreeFuzzer(4242)
+    failures = []
+    for index in range(100):
+        text = fuzzer.tree(depth=3).encode()
+        a, b = helpers.ProductNode(gpu, text), helpers.RefNode(ref, text)
+        for dim, got, want in ((2, a.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, index)[0], b.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, index)[0]),
+                               (3, a.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, index)[0], b.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, index)[0]),
+                               (4, a.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0])):
+            if not same(got, want):
+                failures.append((index, dim, text, helpers.compare(got, want)))
+    assert not failures, failures[:5]

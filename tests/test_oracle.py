@@ -99,3 +99,21 @@ def test_port_oracle_slab_rows_equal_whole_grid(port):
     parts = [node.grid3d(0.0, 0.0, 0.0, 12, 10, 9, 3.3, 3.3, 3.3, 1337, rows=(z0 * 10, (z1 - z0) * 10)) for z0, z1 in ((0, 4), (4, 5), (5, 9))]
     assert np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), whole.view(np.uint32))
     assert min(p[1][0] for p in parts) == mm[0] and max(p[1][1] for p in parts) == mm[1]
+
+
+def test_random_trees_port_vs_strict_ref(ref, port):
+    """Fuzz: random trees over all 47 node types (random parameters, hybrids as generators, shared sub-trees) -- the C
+    restatement and the reference's own sources must agree on every output word, in 2D, 3D and 4D."""
+    from tests.fuzz import TreeFuzzer, same
+    fuzzer = TreeFuzzer(20260117)
+    failures = []
+    for index in range(300):
+        text = fuzzer.tree(depth=3).encode()
+        a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
+        assert a.supported, text
+        for dim, got, want in ((2, a.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, index)[0], b.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, index)[0]),
+                               (3, a.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, index)[0], b.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, index)[0]),
+                               (4, a.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, index)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, index)[0])):
+            if not same(got, want):
+                failures.append((index, dim, text, helpers.compare(got, want)))
+    assert not failures, failures[:5]
