@@ -93,7 +93,9 @@ class Generator:
     # ---- reference-shaped calls (host numpy arrays or device tensors), return (min, max)
     @staticmethod
     def _checked(mm):
-        if not (mm[0] <= mm[1]):
+        # min > max is the failure convention, but it is also what an all-NaN output leaves behind (NaNs are skipped):
+        # the error text, cleared at the start of every Gen* call, tells the two apart
+        if not (mm[0] <= mm[1]) and last_error():
             raise RuntimeError("generation failed: " + last_error())
         return float(mm[0]), float(mm[1])
 

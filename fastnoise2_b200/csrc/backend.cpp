@@ -587,6 +587,7 @@ namespace FastNoise
         OutputMinMax GenGrid( const Generator* root, const GridCall& call, float* out )
         {
             OutputMinMax failed;
+            tLastError.clear(); // an all-NaN output also leaves min > max: callers tell the two apart by the error text
             const int dims = call.kind == kTileable2D ? 2 : call.kind;
             long long rows = 1;
             for( int d = 0; d < dims; d++ )
@@ -651,6 +652,7 @@ namespace FastNoise
         OutputMinMax GenPositions( const Generator* root, int dims, float* out, long long count, const float* const pos[4], const float offset[4], int seed )
         {
             OutputMinMax failed;
+            tLastError.clear();
             if( count <= 0 || !out )
             {
                 SetLastError( count <= 0 ? "count must be positive" : "output pointer is null" );

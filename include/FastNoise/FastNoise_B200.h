@@ -30,7 +30,8 @@ enum
     FNB200_EUNSUPPORTED = -4 /* tree contains a node type this build cannot lower */
 };
 
-/* Thread-local description of the last failure in this library ("" if none). */
+/* Thread-local description of the last failure in this library. Every Gen* call clears it on entry, so "" after a call
+ * that returned min > max means the output is genuine (every value NaN), not a failure. */
 FASTNOISE_API const char* fnb200LastError( void );
 
 /* 1 if a usable CUDA device (compute capability 10.x) and NVRTC are present. Never throws. */

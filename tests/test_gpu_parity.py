@@ -369,4 +369,11 @@ def test_random_trees_vs_strict_oracle(gpu, ref):
                                (4, a.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0])):
             if not same(got, want):
                 failures.append((index, dim, text, helpers.compare(got, want)))
+        if index % 4 == 0:                          # the other two entry kinds: scattered positions and the torus mapping
+            rng = np.random.default_rng(index)
+            pos = [rng.uniform(-300, 300, 1537).astype(np.float32) for _ in range(3)]
+            if not same(a.positions(pos, [0.5, -1.5, 2.5], index)[0], b.positions(pos, [0.5, -1.5, 2.5], index)[0]):
+                failures.append((index, "positions3d", text))
+            if not same(a.tileable2d(40, 24, 1.3, 0.9, index)[0], b.tileable2d(40, 24, 1.3, 0.9, index)[0]):
+                failures.append((index, "tileable2d", text))
     assert not failures, failures[:5]
