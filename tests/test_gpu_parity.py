@@ -377,3 +377,44 @@ def test_random_trees_vs_strict_oracle(gpu, ref):
             if not same(a.tileable2d(40, 24, 1.3, 0.9, index)[0], b.tileable2d(40, 24, 1.3, 0.9, index)[0]):
                 failures.append((index, "tileable2d", text))
     assert not failures, failures[:5]
+
+
+def test_concurrent_calls_from_threads(gpu):
+    """The reference's Gen* methods are const and thread-safe; here every calling thread owns its streams, staging buffers
+    and min/max accumulator. Eight threads hammer two shared generators (host and device destinations, first use compiles
+    concurrently) and every result must equal the single-threaded one."""
+    import threading
+    import torch
+    gens = [gpu.Generator(gpu.TREES["c4_terrain"]), gpu.Generator(gpu.TREES["c3a_cellular_distance"])]
+    shapes = [(40, 24, 16), (33, 17, 9)]
+    expected = {}
+    for gi, g in enumerate(gens):
+        for si, n in enumerate(shapes):
+            out = np.empty(n[0] * n[1] * n[2], np.float32)
+            expected[gi, si] = (out, g.grid3d(out, 1.5, -2.5, 3.5, *n, 0.7, 0.7, 0.7, 99))
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(40):
+                gi, si = (tid + it) % 2, (tid // 2 + it) % 2
+                n = shapes[si]
+                want, want_mm = expected[gi, si]
+                if (tid + it) % 3 == 0:
+                    dev = torch.empty(want.size, dtype=torch.float32, device="cuda")
+                    mm = gens[gi].grid3d(dev, 1.5, -2.5, 3.5, *n, 0.7, 0.7, 0.7, 99)
+                    got = dev.cpu().numpy()
+                else:
+                    got = np.empty(want.size, np.float32)
+                    mm = gens[gi].grid3d(got, 1.5, -2.5, 3.5, *n, 0.7, 0.7, 0.7, 99)
+                if mm != want_mm or not np.array_equal(bits(got), bits(want)):
+                    errors.append((tid, it, gi, si))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
