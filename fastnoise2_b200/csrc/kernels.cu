@@ -61,6 +61,14 @@ namespace
                         f[k] = fmaf( f[k], a, b );
                         u[k] = ( u[k] ^ m ) & ( u[( k + 1 ) & 7] | 0x55555555u );
                     }
+                    if( MODE >= 4 && ( k & 1 ) == 0 )                                 // packed FP32: one FFMA2 per pair of chains
+                    {
+                        const float2 r = __ffma2_rn( make_float2( f[k], f[k + 1] ), make_float2( a, a ), make_float2( b, b ) );
+                        f[k] = r.x;
+                        f[k + 1] = r.y;
+                    }
+                    if( MODE == 5 && ( k & 1 ) == 0 ) u[k] = ( u[k] ^ m ) & ( u[( k + 2 ) & 7] | 0x55555555u );   // + 1 LOP3 per FFMA2
+                    if( MODE == 6 ) u[k] = ( u[k] ^ m ) & ( u[( k + 1 ) & 7] | 0x55555555u );                     // + 2 LOP3 per FFMA2
                 }
             }
         }
@@ -102,7 +110,10 @@ namespace FastNoise
                 case 0: AluProbeKernel<0><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 case 1: AluProbeKernel<1><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 case 2: AluProbeKernel<2><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
-                default: AluProbeKernel<3><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 3: AluProbeKernel<3><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 4: AluProbeKernel<4><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 5: AluProbeKernel<5><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                default: AluProbeKernel<6><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 }
             };
             launch( 16 ); // warm-up
@@ -116,7 +127,8 @@ namespace FastNoise
                 cudaEventSynchronize( t1 );
                 float ms = 0;
                 cudaEventElapsedTime( &ms, t0, t1 );
-                const double opsPerThread = (double)iters * 16 * 8 * ( mode == 3 ? 2 : 1 );
+                const double perRep = mode == 3 ? 16 : ( mode == 5 ? 12 : ( mode == 6 ? 16 : 8 ) ); // lane-operations per repetition (an FFMA2 counts as 2)
+                const double opsPerThread = (double)iters * 16 * perRep;
                 const double rate = opsPerThread * blocks * 256 / ( ms * 1e-3 );
                 if( ms > 0 && rate > best ) best = rate;
             }
