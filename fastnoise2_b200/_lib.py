@@ -69,6 +69,7 @@ PROTOTYPES = {
     "fnb200Prepare": (I, [P, I]),
     "fnb200GetKernelSource": (ctypes.c_long, [P, I, P, ctypes.c_long]),
     "fnb200SelfTestInvSqrt": (LL, [F, F]),
+    "fnb200SelfTestLeaf": (I, [I, I, I, I, F, P]),
     "fnb200MinMaxReset": (I, [P, P]),
     "fnb200MinMaxRead": (I, [P, P, P]),
     "fnb200GenUniformGrid2D": (I, [P, P, F, F, I, I, F, F, I, I, I, P, P]),

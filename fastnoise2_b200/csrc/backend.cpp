@@ -472,6 +472,7 @@ namespace FastNoise
 
         static int PointsPerThreadFor( unsigned long long points, int ppt )
         {
+            if( EnvInt( "FASTNOISE2_B200_FILL", 1 ) == 0 ) return ppt; // tests: keep the large-call code path for small calls
             while( ppt > 1 && points / (unsigned)ppt < ResidentThreads() ) ppt >>= 1;
             return ppt;
         }

@@ -51,6 +51,7 @@ namespace FastNoise
 
         const std::string& LastError();
         long long SelfTestInvSqrt( float lo, float hi ); // device_check.cu
+        int SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut ); // device_check.cu
         int MathMode();
         void SetMathMode( int mode );
         unsigned long long LaunchCount();

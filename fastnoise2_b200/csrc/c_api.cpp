@@ -377,4 +377,5 @@ extern "C"
 
     double fnb200MeasureAluPeak( int mode, int iters ) { return Impl::MeasureAluPeak( mode, iters ); }
     long long fnb200SelfTestInvSqrt( float lo, float hi ) { return Impl::SelfTestInvSqrt( lo, hi ); }
+    int fnb200SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut ) { return Impl::SelfTestLeaf( packed, which, n, seed, step, hostOut ); }
 }

@@ -21,27 +21,34 @@ namespace fn2
     constexpr float kSizeJitterScale4D = -1.f / 0xfffff;
     constexpr float kFltMax = 3.402823466e+38f;
 
-    FN2_DI i32 lsr( i32 v, int s ) { return (i32)( (u32)v >> s ); } // FS::BitShiftRightZeroExtend
-
     // Jitter direction of a cell from its hash and the factor that scales it to length `jitter`.
     // [Cellular.inl:57-60] 2D: two 11-bit fields
-    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd )
+    template<class F>
+    FN2_DI F cell_vector( typename pack<F>::I hash, F jitter, F& xd, F& yd )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         xd = cvt_f( hash & 0x7ff ) - ( 0x7ff / 2.0f );
         yd = cvt_f( lsr( hash, 21 ) ) - ( 0x7ff / 2.0f );
         return jitter * inv_sqrt_bounded( fma_( xd, xd, yd * yd ) );
     }
     // [Cellular.inl:148-152] 3D: three 10-bit fields at bits 0, 11, 22
-    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd )
+    template<class F>
+    FN2_DI F cell_vector( typename pack<F>::I hash, F jitter, F& xd, F& yd, F& zd )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         xd = cvt_f( hash & 0x3ff ) - ( 0x3ff / 2.0f );
         yd = field_minus<11, 10>( hash, 0x3ff / 2.0f );
         zd = cvt_f( lsr( hash, 22 ) ) - ( 0x3ff / 2.0f );
         return jitter * inv_sqrt_bounded( fma_( xd, xd, fma_( yd, yd, zd * zd ) ) );
     }
     // [Cellular.inl:247-252] 4D: four bytes
-    FN2_DI float cell_vector( i32 hash, float jitter, float& xd, float& yd, float& zd, float& wd )
+    template<class F>
+    FN2_DI F cell_vector( typename pack<F>::I hash, F jitter, F& xd, F& yd, F& zd, F& wd )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         xd = cvt_f( hash & 0xff ) - ( 0xff / 2.0f );
         yd = field_minus<8, 8>( hash, 0xff / 2.0f );
         zd = cvt_f( ( hash >> 16 ) & 0xff ) - ( 0xff / 2.0f );
@@ -50,31 +57,38 @@ namespace fn2
     }
 
     // per-cell distance multiplier of the size jitter [Cellular.inl:66-70, 160-164, 260-264]
-    FN2_DI float size_jitter2( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, field_f<11, 10>( hash ), 1.0f ); }
-    FN2_DI float size_jitter3( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xffff ), 1.0f ); }
-    FN2_DI float size_jitter4( i32 hash, float sizeJitter ) { return fnma_( sizeJitter, cvt_f( hash & 0xfffff ), 1.0f ); }
+    template<class F>
+    FN2_DI F size_jitter2( typename pack<F>::I hash, F sizeJitter ) { typedef typename pack<F>::I I; typedef typename pack<F>::B B; (void)sizeof( I ); (void)sizeof( B ); return fnma_( sizeJitter, field_f<11, 10>( hash ), 1.0f ); }
+    template<class F>
+    FN2_DI F size_jitter3( typename pack<F>::I hash, F sizeJitter ) { typedef typename pack<F>::I I; typedef typename pack<F>::B B; (void)sizeof( I ); (void)sizeof( B ); return fnma_( sizeJitter, cvt_f( hash & 0xffff ), 1.0f ); }
+    template<class F>
+    FN2_DI F size_jitter4( typename pack<F>::I hash, F sizeJitter ) { typedef typename pack<F>::I I; typedef typename pack<F>::B B; (void)sizeof( I ); (void)sizeof( B ); return fnma_( sizeJitter, cvt_f( hash & 0xfffff ), 1.0f ); }
 
     // insert into the ascending (distance, hash) list, entries 0..TOP [Cellular.inl:72-89]
-    template<int TOP>
-    FN2_DI void value_insert( float ( &distance )[4], i32 ( &valueHash )[4], float newDistance, i32 newHash )
+    template<int TOP, class F>
+    FN2_DI void value_insert( F ( &distance )[4], typename pack<F>::I ( &valueHash )[4], F newDistance, typename pack<F>::I newHash )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
 #pragma unroll
         for( int i = 0; i <= TOP; i++ )
         {
-            bool closer = newDistance < distance[i];
-            float localDistance = distance[i];
-            i32 localHash = valueHash[i];
-            distance[i] = closer ? newDistance : distance[i];
-            valueHash[i] = closer ? newHash : valueHash[i];
-            newDistance = closer ? localDistance : newDistance;
-            newHash = closer ? localHash : newHash;
+            B closer = newDistance < distance[i];
+            F localDistance = distance[i];
+            I localHash = valueHash[i];
+            distance[i] = select( closer, newDistance, distance[i] );
+            valueHash[i] = select( closer, newHash, valueHash[i] );
+            newDistance = select( closer, localDistance, newDistance );
+            newHash = select( closer, localHash, newHash );
         }
     }
 
     // sorting network step of CellularDistance, entries 0..TOP [Cellular.inl:344-349]
-    template<int TOP>
-    FN2_DI void distance_insert( float ( &distance )[4], float newDistance )
+    template<int TOP, class F>
+    FN2_DI void distance_insert( F ( &distance )[4], F newDistance )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
 #pragma unroll
         for( int i = TOP; i > 0; i-- )
         {
@@ -85,29 +99,31 @@ namespace fn2
 
     // ================================================================== CellularValue [Cellular.inl:18-292]
     // returns the hash of the TOP-th closest cell (caller converts and range-maps it)
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI i32 cellular_value2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI typename pack<F>::I cellular_value2( i32 seed, F x, F y, F jitter, F sizeJitter, PF minkowskiP )
     {
-        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
-        i32 valueHash[4] = { 0, 0, 0, 0 };
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        I valueHash[4] = { 0, 0, 0, 0 };
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
-        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y;
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        F xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y;
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                i32 hash = hash_hb( seed, xc, yc );
-                float xd, yd;
-                float invMag = cell_vector( hash, jitter, xd, yd );
+                I hash = hash_hb( seed, xc, yc );
+                F xd, yd;
+                F invMag = cell_vector( hash, jitter, xd, yd );
                 xd = fma_( xd, invMag, xcf );
                 yd = fma_( yd, invMag, ycf );
-                float newDistance = calc_distance<DF, true>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                F newDistance = calc_distance<DF, true>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
                 if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
                 value_insert<TOP>( distance, valueHash, newDistance, hash );
                 ycf += 1.0f;
@@ -119,35 +135,37 @@ namespace fn2
         return valueHash[TOP];
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI i32 cellular_value3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI typename pack<F>::I cellular_value3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP )
     {
-        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
-        i32 valueHash[4] = { 0, 0, 0, 0 };
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        I valueHash[4] = { 0, 0, 0, 0 };
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
-        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z;
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        F xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z;
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    i32 hash = hash_hb( seed, xc, yc, zc );
-                    float xd, yd, zd;
-                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    I hash = hash_hb( seed, xc, yc, zc );
+                    F xd, yd, zd;
+                    F invMag = cell_vector( hash, jitter, xd, yd, zd );
                     xd = fma_( xd, invMag, xcf );
                     yd = fma_( yd, invMag, ycf );
                     zd = fma_( zd, invMag, zcf );
-                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
                     if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
                     value_insert<TOP>( distance, valueHash, newDistance, hash );
                     zcf += 1.0f;
@@ -162,14 +180,16 @@ namespace fn2
         return valueHash[TOP];
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI i32 cellular_value4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI typename pack<F>::I cellular_value4( i32 seed, F x, F y, F z, F w, F jitter, F sizeJitter, PF minkowskiP )
     {
-        float distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
-        i32 valueHash[4] = { 0, 0, 0, 0 };
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance[4] = { FN2_INF, FN2_INF, FN2_INF, FN2_INF };
+        I valueHash[4] = { 0, 0, 0, 0 };
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
-        float xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z, wcfBase = cvt_f( wcBase ) - w;
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        F xcf = cvt_f( xc ) - x, ycfBase = cvt_f( ycBase ) - y, zcfBase = cvt_f( zcBase ) - z, wcfBase = cvt_f( wcBase ) - w;
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
@@ -177,26 +197,26 @@ namespace fn2
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    float wcf = wcfBase;
-                    i32 wc = wcBase;
+                    F wcf = wcfBase;
+                    I wc = wcBase;
                     for( int wi = 0; wi < 3; wi++ )
                     {
-                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
-                        float xd, yd, zd, wd;
-                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        I hash = hash_hb( seed, xc, yc, zc, wc );
+                        F xd, yd, zd, wd;
+                        F invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
                         xd = fma_( xd, invMag, xcf );
                         yd = fma_( yd, invMag, ycf );
                         zd = fma_( zd, invMag, zcf );
                         wd = fma_( wd, invMag, wcf );
-                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
                         if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
                         value_insert<TOP>( distance, valueHash, newDistance, hash );
                         wcf += 1.0f;
@@ -216,29 +236,31 @@ namespace fn2
 
     // ================================================================== CellularDistance [Cellular.inl:295-529]
     // fills distance[0..TOP] with the ascending cell distances
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI void cellular_distance2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI void cellular_distance2( i32 seed, F x, F y, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float xcfOffset = xcf - x;
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F xcfOffset = xcf - x;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                i32 hash = hash_hb( seed, xc, yc );
-                float xd, yd;
-                float invMag = cell_vector( hash, jitter, xd, yd );
+                I hash = hash_hb( seed, xc, yc );
+                F xd, yd;
+                F invMag = cell_vector( hash, jitter, xd, yd );
                 xd = fma_( xd, invMag, xcfOffset );
                 yd = fma_( yd, invMag, ycf - y );
-                float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
                 if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
                 distance_insert<TOP>( distance, newDistance );
                 ycf += 1.0f;
@@ -249,36 +271,38 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI void cellular_distance3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI void cellular_distance3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float xcfOffset = xcf - x;
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F xcfOffset = xcf - x;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float ycfOffset = ycf - y;
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F ycfOffset = ycf - y;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    i32 hash = hash_hb( seed, xc, yc, zc );
-                    float xd, yd, zd;
-                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    I hash = hash_hb( seed, xc, yc, zc );
+                    F xd, yd, zd;
+                    F invMag = cell_vector( hash, jitter, xd, yd, zd );
                     xd = fma_( xd, invMag, xcfOffset );
                     yd = fma_( yd, invMag, ycfOffset );
                     zd = fma_( zd, invMag, zcf - z );
-                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
                     if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
                     distance_insert<TOP>( distance, newDistance );
                     zcf += 1.0f;
@@ -292,13 +316,15 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF>
-    FN2_DI void cellular_distance4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP, float ( &distance )[4] )
+    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    FN2_DI void cellular_distance4( i32 seed, F x, F y, F z, F w, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         distance[0] = distance[1] = distance[2] = distance[3] = FN2_INF;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
@@ -306,29 +332,29 @@ namespace fn2
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float xcfOffset = xcf - x;
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F xcfOffset = xcf - x;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float ycfOffset = ycf - y;
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F ycfOffset = ycf - y;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    float zcfOffset = zcf - z;
-                    float wcf = wcfBase;
-                    i32 wc = wcBase;
+                    F zcfOffset = zcf - z;
+                    F wcf = wcfBase;
+                    I wc = wcBase;
                     for( int wi = 0; wi < 3; wi++ )
                     {
-                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
-                        float xd, yd, zd, wd;
-                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        I hash = hash_hb( seed, xc, yc, zc, wc );
+                        F xd, yd, zd, wd;
+                        F invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
                         xd = fma_( xd, invMag, xcfOffset );
                         yd = fma_( yd, invMag, ycfOffset );
                         zd = fma_( zd, invMag, zcfOffset );
                         wd = fma_( wd, invMag, wcf - w );
-                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
                         if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
                         distance_insert<TOP>( distance, newDistance );
                         wcf += 1.0f;
@@ -347,36 +373,38 @@ namespace fn2
 
     // ================================================================== CellularLookup [Cellular.inl:569-806]
     // writes the jittered centre of the closest cell
-    template<int DF, bool SIZEJ, class PF>
-    FN2_DI void cellular_lookup2( i32 seed, float x, float y, float jitter, float sizeJitter, PF minkowskiP, float& cellX, float& cellY )
+    template<int DF, bool SIZEJ, class PF, class F>
+    FN2_DI void cellular_lookup2( i32 seed, F x, F y, F jitter, F sizeJitter, PF minkowskiP, F& cellX, F& cellY )
     {
-        float distance = kFltMax;
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance = kFltMax;
         cellX = cellY = 0.0f;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                i32 hash = hash_hb( seed, xc, yc );
-                float xd, yd;
-                float invMag = cell_vector( hash, jitter, xd, yd );
-                float localX = fma_( xd, invMag, xcf );
-                float localY = fma_( yd, invMag, ycf );
+                I hash = hash_hb( seed, xc, yc );
+                F xd, yd;
+                F invMag = cell_vector( hash, jitter, xd, yd );
+                F localX = fma_( xd, invMag, xcf );
+                F localY = fma_( yd, invMag, ycf );
                 xd = localX - x;
                 yd = localY - y;
-                float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
+                F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
                 if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
-                bool closer = newDistance < distance;
+                B closer = newDistance < distance;
                 distance = min_( newDistance, distance );
-                cellX = closer ? localX : cellX;
-                cellY = closer ? localY : cellY;
+                cellX = select( closer, localX, cellX );
+                cellY = select( closer, localY, cellY );
                 ycf += 1.0f;
                 yc = iadd( yc, kPY );
             }
@@ -385,44 +413,46 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, class PF>
-    FN2_DI void cellular_lookup3( i32 seed, float x, float y, float z, float jitter, float sizeJitter, PF minkowskiP, float& cellX, float& cellY, float& cellZ )
+    template<int DF, bool SIZEJ, class PF, class F>
+    FN2_DI void cellular_lookup3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP, F& cellX, F& cellY, F& cellZ )
     {
-        float distance = kFltMax;
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance = kFltMax;
         cellX = cellY = cellZ = 0.0f;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    i32 hash = hash_hb( seed, xc, yc, zc );
-                    float xd, yd, zd;
-                    float invMag = cell_vector( hash, jitter, xd, yd, zd );
-                    float localX = fma_( xd, invMag, xcf );
-                    float localY = fma_( yd, invMag, ycf );
-                    float localZ = fma_( zd, invMag, zcf );
+                    I hash = hash_hb( seed, xc, yc, zc );
+                    F xd, yd, zd;
+                    F invMag = cell_vector( hash, jitter, xd, yd, zd );
+                    F localX = fma_( xd, invMag, xcf );
+                    F localY = fma_( yd, invMag, ycf );
+                    F localZ = fma_( zd, invMag, zcf );
                     xd = localX - x;
                     yd = localY - y;
                     zd = localZ - z;
-                    float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
+                    F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
                     if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
-                    bool closer = newDistance < distance;
+                    B closer = newDistance < distance;
                     distance = min_( newDistance, distance );
-                    cellX = closer ? localX : cellX;
-                    cellY = closer ? localY : cellY;
-                    cellZ = closer ? localZ : cellZ;
+                    cellX = select( closer, localX, cellX );
+                    cellY = select( closer, localY, cellY );
+                    cellZ = select( closer, localZ, cellZ );
                     zcf += 1.0f;
                     zc = iadd( zc, kPZ );
                 }
@@ -434,15 +464,17 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, class PF>
-    FN2_DI void cellular_lookup4( i32 seed, float x, float y, float z, float w, float jitter, float sizeJitter, PF minkowskiP,
-                                  float& cellX, float& cellY, float& cellZ, float& cellW )
+    template<int DF, bool SIZEJ, class PF, class F>
+    FN2_DI void cellular_lookup4( i32 seed, F x, F y, F z, F w, F jitter, F sizeJitter, PF minkowskiP,
+                                  F& cellX, F& cellY, F& cellZ, F& cellW )
     {
-        float distance = kFltMax;
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F distance = kFltMax;
         cellX = cellY = cellZ = cellW = 0.0f;
 
-        i32 xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
-        float xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
+        I xc = iadd( cvt_i( x ), -1 ), ycBase = iadd( cvt_i( y ), -1 ), zcBase = iadd( cvt_i( z ), -1 ), wcBase = iadd( cvt_i( w ), -1 );
+        F xcf = cvt_f( xc ), ycfBase = cvt_f( ycBase ), zcfBase = cvt_f( zcBase ), wcfBase = cvt_f( wcBase );
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
@@ -450,37 +482,37 @@ namespace fn2
 
         for( int xi = 0; xi < 3; xi++ )
         {
-            float ycf = ycfBase;
-            i32 yc = ycBase;
+            F ycf = ycfBase;
+            I yc = ycBase;
             for( int yi = 0; yi < 3; yi++ )
             {
-                float zcf = zcfBase;
-                i32 zc = zcBase;
+                F zcf = zcfBase;
+                I zc = zcBase;
                 for( int zi = 0; zi < 3; zi++ )
                 {
-                    float wcf = wcfBase;
-                    i32 wc = wcBase;
+                    F wcf = wcfBase;
+                    I wc = wcBase;
                     for( int wi = 0; wi < 3; wi++ )
                     {
-                        i32 hash = hash_hb( seed, xc, yc, zc, wc );
-                        float xd, yd, zd, wd;
-                        float invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
-                        float localX = fma_( xd, invMag, xcf );
-                        float localY = fma_( yd, invMag, ycf );
-                        float localZ = fma_( zd, invMag, zcf );
-                        float localW = fma_( wd, invMag, wcf );
+                        I hash = hash_hb( seed, xc, yc, zc, wc );
+                        F xd, yd, zd, wd;
+                        F invMag = cell_vector( hash, jitter, xd, yd, zd, wd );
+                        F localX = fma_( xd, invMag, xcf );
+                        F localY = fma_( yd, invMag, ycf );
+                        F localZ = fma_( zd, invMag, zcf );
+                        F localW = fma_( wd, invMag, wcf );
                         xd = localX - x;
                         yd = localY - y;
                         zd = localZ - z;
                         wd = localW - w;
-                        float newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
+                        F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
                         if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
-                        bool closer = newDistance < distance;
+                        B closer = newDistance < distance;
                         distance = min_( newDistance, distance );
-                        cellX = closer ? localX : cellX;
-                        cellY = closer ? localY : cellY;
-                        cellZ = closer ? localZ : cellZ;
-                        cellW = closer ? localW : cellW;
+                        cellX = select( closer, localX, cellX );
+                        cellY = select( closer, localY, cellY );
+                        cellZ = select( closer, localZ, cellZ );
+                        cellW = select( closer, localW, cellW );
                         wcf += 1.0f;
                         wc = iadd( wc, kPW );
                     }

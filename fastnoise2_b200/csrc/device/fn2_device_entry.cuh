@@ -84,6 +84,22 @@ namespace fn2
         }
     }
 
+    // width-generic glue between the per-point arrays of the entry kernels and the value type of the node functions
+    template<class F> FN2_DI F index_positions( u32 index, float step, float offset );        // fma( float(index + lane), step, offset )
+    template<> __device__ __forceinline__ float index_positions<float>( u32 index, float step, float offset ) { return fma_( cvt_f( (i32)index ), step, offset ); }
+    template<> __device__ __forceinline__ fpair index_positions<fpair>( u32 index, float step, float offset )
+    {
+        return fma_( fpair( cvt_f( (i32)index ), cvt_f( (i32)( index + 1u ) ) ), fpair( step ), fpair( offset ) );
+    }
+    template<class F> FN2_DI F index_positions( u32 index, float scale );                      // float(index + lane) * scale
+    template<> __device__ __forceinline__ float index_positions<float>( u32 index, float scale ) { return cvt_f( (i32)index ) * scale; }
+    template<> __device__ __forceinline__ fpair index_positions<fpair>( u32 index, float scale ) { return fpair( cvt_f( (i32)index ), cvt_f( (i32)( index + 1u ) ) ) * fpair( scale ); }
+    template<class F> FN2_DI F lane_values( const float* v );
+    template<> __device__ __forceinline__ float lane_values<float>( const float* v ) { return v[0]; }
+    template<> __device__ __forceinline__ fpair lane_values<fpair>( const float* v ) { return fpair( v[0], v[1] ); }
+    FN2_DI void spill_lanes( float r, float* v ) { v[0] = r; }
+    FN2_DI void spill_lanes( fpair r, float* v ) { v[0] = r.x; v[1] = r.y; }
+
     template<int P>
     FN2_DI void store_points( float* __restrict__ out, u32 first, const float ( &v )[P], bool vec )
     {

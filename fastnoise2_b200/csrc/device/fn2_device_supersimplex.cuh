@@ -10,77 +10,87 @@ namespace fn2
     constexpr float kSuperSimplexBound4 = (float)0.011310013942420482635498046875;
 
     FN2_DI float sq2( float v ) { return ( v * v ) * ( v * v ); }
-    FN2_DI i32 signbit_if( bool c ) { return c ? (i32)0x80000000u : 0; }
+    FN2_DI fpair sq2( fpair v ) { return ( v * v ) * ( v * v ); }
     // base +- prime, by sign mask [Simplex.inl:475 and siblings]
     FN2_DI i32 step_prime( i32 base, i32 prime, bool negative ) { return iadd( base, negative ? isub( 0, prime ) : prime ); }
+    FN2_DI ipair step_prime( ipair base, i32 prime, bpair negative ) { return ipair( step_prime( base.x, prime, negative.x ), step_prime( base.y, prime, negative.y ) ); }
 
     // Vertex producers shared with DomainWarpSuperSimplex [DomainWarpSimplex.inl:1133-1833 repeats the geometry below],
     // vertices in the reference's accumulation order, falloff already raised to the 4th power.
     // [Simplex.inl:293-377]
-    FN2_DI void supersimplex2_vertices( i32 seed, float x, float y, Verts2 ( &v )[4] )
+    template<class F>
+    FN2_DI void supersimplex2_vertices( i32 seed, F x, F y, Verts2<F> ( &v )[4] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         constexpr double kSkew2 = 1.0 / ( kRoot3 + 1.0 );
         constexpr double kUnskew2 = -1.0 / ( kRoot3 + 3.0 );
         constexpr float kR2 = (float)( 2.0 / 3.0 );
 
-        float skewDelta = (float)kSkew2 * ( x + y );
-        float xSkewed = x + skewDelta, ySkewed = y + skewDelta;
-        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed );
-        float dxS = xSkewed - xBase, dyS = ySkewed - yBase;
-        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY );
+        F skewDelta = (float)kSkew2 * ( x + y );
+        F xSkewed = x + skewDelta, ySkewed = y + skewDelta;
+        F xBase = floor_( xSkewed ), yBase = floor_( ySkewed );
+        F dxS = xSkewed - xBase, dyS = ySkewed - yBase;
+        I xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY );
 
-        bool forwardXY = dxS + dyS > 1.0f;
-        float boundaryXY = forwardXY ? -1.0f : 0.0f;
-        bool forwardX = fma_( dxS, -2.0f, dyS ) < boundaryXY;
-        bool forwardY = fma_( dyS, -2.0f, dxS ) < boundaryXY;
+        B forwardXY = dxS + dyS > 1.0f;
+        F boundaryXY = select( forwardXY, F( -1.0f ), F( 0.0f ) );
+        B forwardX = fma_( dxS, -2.0f, dyS ) < boundaryXY;
+        B forwardY = fma_( dyS, -2.0f, dxS ) < boundaryXY;
 
-        float unskewDelta = (float)kUnskew2 * ( dxS + dyS );
-        float dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
+        F unskewDelta = (float)kUnskew2 * ( dxS + dyS );
+        F dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
 
-        float falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
+        F falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
         v[0] = { hash_hb( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
         { // vertex <1,1>
-            float falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
+            F falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
             v[1] = { hash_hb( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
         }
 
-        float xyDelta = forwardXY ? (float)( kUnskew2 + 1 ) : (float)( -kUnskew2 );
+        F xyDelta = select( forwardXY, F( (float)( kUnskew2 + 1 ) ), F( (float)( -kUnskew2 ) ) );
         dxBase -= xyDelta;
         dyBase -= xyDelta;
 
         { // vertex <1,0> or <-1,0> or <1,2>
-            i32 xv = forwardX ? iadd( xP, imul( kPX, 2 ) ) : xP;
-            xv = forwardXY ? xv : isub( xv, kPX );
-            i32 yv = forwardXY ? iadd( yP, kPY ) : yP;
-            float dx = dxBase - ( forwardX ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
-            float dy = forwardX ? dyBase - (float)( 2 * kUnskew2 ) : dyBase;
-            float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
+            I xv = select( forwardX, iadd( xP, imul( kPX, 2 ) ), xP );
+            xv = select( forwardXY, xv, isub( xv, kPX ) );
+            I yv = select( forwardXY, iadd( yP, kPY ), yP );
+            F dx = dxBase - ( select( forwardX, F( (float)( 1 + 2 * kUnskew2 ) ), F( -1.0f ) ));
+            F dy = select( forwardX, dyBase - (float)( 2 * kUnskew2 ), dyBase );
+            F falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
             v[2] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
         { // vertex <0,1> or <0,-1> or <2,1>
-            i32 xv = forwardXY ? iadd( xP, kPX ) : xP;
-            i32 yv = forwardY ? iadd( yP, imul( kPY, 2 ) ) : yP;
-            yv = forwardXY ? yv : isub( yv, kPY );
-            float dx = forwardY ? dxBase - (float)( 2 * kUnskew2 ) : dxBase;
-            float dy = dyBase - ( forwardY ? (float)( 1 + 2 * kUnskew2 ) : -1.0f );
-            float falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
+            I xv = select( forwardXY, iadd( xP, kPX ), xP );
+            I yv = select( forwardY, iadd( yP, imul( kPY, 2 ) ), yP );
+            yv = select( forwardXY, yv, isub( yv, kPY ) );
+            F dx = select( forwardY, dxBase - (float)( 2 * kUnskew2 ), dxBase );
+            F dy = dyBase - ( select( forwardY, F( (float)( 1 + 2 * kUnskew2 ) ), F( -1.0f ) ));
+            F falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
             v[3] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
     }
 
-    FN2_DI float supersimplex2( i32 seed, float x, float y )
+    template<class F>
+    FN2_DI F supersimplex2( i32 seed, F x, F y )
     {
-        Verts2 v[4];
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        Verts2<F> v[4];
         supersimplex2_vertices( seed, x, y, v );
-        float value = v[0].falloff * grad_dot2( v[0].hb, v[0].dx, v[0].dy );
+        F value = v[0].falloff * grad_dot2( v[0].hb, v[0].dx, v[0].dy );
 #pragma unroll
         for( int k = 1; k < 4; k++ ) value = fma_( v[k].falloff, grad_dot2( v[k].hb, v[k].dx, v[k].dy ), value );
         return value;
     }
 
     // [Simplex.inl:379-576]
-    FN2_DI void supersimplex3_vertices( i32 seed, float x, float y, float z, Verts3 ( &v )[8] )
+    template<class F>
+    FN2_DI void supersimplex3_vertices( i32 seed, F x, F y, F z, Verts3<F> ( &v )[8] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         constexpr double kSkew3 = 1.0 / 3.0;
         constexpr double kReflectUnskew3 = -1.0 / 2.0;
         constexpr double kTwiceUnskew3 = -1.0 / 4.0;
@@ -88,20 +98,20 @@ namespace fn2
         constexpr double kDistanceSquaredB = 1.0;
         constexpr float kR2 = (float)kDistanceSquaredA;
 
-        float skewDelta = (float)kSkew3 * ( x + y + z );
-        float xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta;
-        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed );
-        float dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase;
+        F skewDelta = (float)kSkew3 * ( x + y + z );
+        F xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta;
+        F xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed );
+        F dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase;
 
         { // closest lattice vertex of the unit cell [:405-441]
-            float tud = (float)kTwiceUnskew3 * ( dxS + dyS + dzS );
-            float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
-            float xyzN = -tud;
+            F tud = (float)kTwiceUnskew3 * ( dxS + dyS + dzS );
+            F xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
+            F xyzN = -tud;
 
-            float maxScore = 0.375f;
-            i32 bits = xyzN > maxScore ? -1 : 0;
+            F maxScore = 0.375f;
+            I bits = select( xyzN > maxScore, I( -1 ), I( 0 ) );
             maxScore = max_( maxScore, xyzN );
-#define FN2_CONSIDER( SCORE, BITS ) { float sc = SCORE; bits = sc > maxScore ? BITS : bits; maxScore = max_( maxScore, sc ); }
+#define FN2_CONSIDER( SCORE, BITS ) { F sc = SCORE; bits = select( sc > maxScore, BITS, bits ); maxScore = max_( maxScore, sc ); }
             FN2_CONSIDER( xN, 1 )
             FN2_CONSIDER( yN, 2 )
             FN2_CONSIDER( zN, 4 )
@@ -110,97 +120,103 @@ namespace fn2
             FN2_CONSIDER( -yN, 5 )
             FN2_CONSIDER( -xN, 6 )
 
-            bool moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0;
-            xBase = moveX ? xBase + 1.0f : xBase;
-            yBase = moveY ? yBase + 1.0f : yBase;
-            zBase = moveZ ? zBase + 1.0f : zBase;
-            dxS = moveX ? dxS - 1.0f : dxS;
-            dyS = moveY ? dyS - 1.0f : dyS;
-            dzS = moveZ ? dzS - 1.0f : dzS;
+            B moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0;
+            xBase = select( moveX, xBase + 1.0f, xBase );
+            yBase = select( moveY, yBase + 1.0f, yBase );
+            zBase = select( moveZ, zBase + 1.0f, zBase );
+            dxS = select( moveX, dxS - 1.0f, dxS );
+            dyS = select( moveY, dyS - 1.0f, dyS );
+            dzS = select( moveZ, dzS - 1.0f, dzS );
         }
 
-        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ );
+        I xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ );
 
-        float sum = dxS + dyS + dzS;
-        float tud = (float)kTwiceUnskew3 * sum;
-        float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
-        float xyzN = -tud;
+        F sum = dxS + dyS + dzS;
+        F tud = (float)kTwiceUnskew3 * sum;
+        F xN = dxS + tud, yN = dyS + tud, zN = dzS + tud;
+        F xyzN = -tud;
 
-        float ud = (float)kReflectUnskew3 * sum;
-        float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud;
-        float coordSum = (float)( 1 + 3 * kReflectUnskew3 ) * sum;
+        F ud = (float)kReflectUnskew3 * sum;
+        F dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud;
+        F coordSum = (float)( 1 + 3 * kReflectUnskew3 ) * sum;
 
-        float stemA, stemB;
+        F stemA, stemB;
         { // <0,0,0>
-            float fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
+            F fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
             v[0] = { hash_hb( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
         }
         { // <1,1,1> or <-1,-1,-1>
-            bool sm = xyzN < 0.0f;
-            i32 sign = signbit_if( sm );
-            float o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
-            float fb = max_( fma_( o, coordSum, stemA ), 0.0f );
+            B sm = xyzN < 0.0f;
+            I sign = signbit_if( sm );
+            F o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
+            F fb = max_( fma_( o, coordSum, stemA ), 0.0f );
             v[1] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
         }
         { // <1,1,0> or <-1,-1,0>
-            bool sm = xyzN < zN;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
+            B sm = xyzN < zN;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            F fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
             v[2] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
         }
         { // <1,0,1> or <-1,0,-1>
-            bool sm = xyzN < yN;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
+            B sm = xyzN < yN;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            F fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
             v[3] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
         }
         { // <0,1,1> or <0,-1,-1>
-            bool sm = xyzN < xN;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            float fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
+            B sm = xyzN < xN;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
+            F fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
             v[4] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
         }
         { // <1,0,0> or <-1,0,0>
-            bool sm = xN < 0.0f;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)kReflectUnskew3, sign );
-            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
+            B sm = xN < 0.0f;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)kReflectUnskew3, sign );
+            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
             v[5] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
         }
         { // <0,1,0> or <0,-1,0>
-            bool sm = yN < 0.0f;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)kReflectUnskew3, sign );
-            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
+            B sm = yN < 0.0f;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)kReflectUnskew3, sign );
+            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
             v[6] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
         }
         { // <0,0,1> or <0,0,-1>
-            bool sm = zN < 0.0f;
-            i32 sign = signbit_if( sm );
-            float o0 = fxor( (float)kReflectUnskew3, sign );
-            float fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
+            B sm = zN < 0.0f;
+            I sign = signbit_if( sm );
+            F o0 = fxor( (float)kReflectUnskew3, sign );
+            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
             v[7] = { hash_hb( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
         }
     }
 
-    FN2_DI float supersimplex3( i32 seed, float x, float y, float z )
+    template<class F>
+    FN2_DI F supersimplex3( i32 seed, F x, F y, F z )
     {
-        Verts3 v[8];
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        Verts3<F> v[8];
         supersimplex3_vertices( seed, x, y, z, v );
-        float value = v[0].falloff * grad_dot3( v[0].hb, v[0].dx, v[0].dy, v[0].dz );
+        F value = v[0].falloff * grad_dot3( v[0].hb, v[0].dx, v[0].dy, v[0].dz );
 #pragma unroll
         for( int k = 1; k < 8; k++ ) value = fma_( v[k].falloff, grad_dot3( v[k].hb, v[k].dx, v[k].dy, v[k].dz ), value );
         return value;
     }
 
     // [Simplex.inl:578-936]
-    FN2_DI void supersimplex4_vertices( i32 seed, float x, float y, float z, float w, Verts4 ( &v )[16] )
+    template<class F>
+    FN2_DI void supersimplex4_vertices( i32 seed, F x, F y, F z, F w, Verts4<F> ( &v )[16] )
     {
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
         constexpr double kSkew4 = 1.0 / ( kRoot5 + 1.0 );
         constexpr double kUnskew4 = -1.0 / ( kRoot5 + 5.0 );
         constexpr double kTwiceUnskew4 = -1.0 / 5.0;
@@ -208,18 +224,18 @@ namespace fn2
         constexpr double kDistanceSquaredB = 6.0 / 5.0;
         constexpr float kR2 = (float)kDistanceSquaredA;
 
-        float skewDelta = (float)kSkew4 * ( x + y + z + w );
-        float xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta, wSkewed = w + skewDelta;
-        float xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed ), wBase = floor_( wSkewed );
-        float dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase, dwS = wSkewed - wBase;
+        F skewDelta = (float)kSkew4 * ( x + y + z + w );
+        F xSkewed = x + skewDelta, ySkewed = y + skewDelta, zSkewed = z + skewDelta, wSkewed = w + skewDelta;
+        F xBase = floor_( xSkewed ), yBase = floor_( ySkewed ), zBase = floor_( zSkewed ), wBase = floor_( wSkewed );
+        F dxS = xSkewed - xBase, dyS = ySkewed - yBase, dzS = zSkewed - zBase, dwS = wSkewed - wBase;
 
         { // closest lattice vertex of the unit cell [:608-659]
-            float tud = (float)kTwiceUnskew4 * ( dxS + dyS + dzS + dwS );
-            float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
-            float xyzwN = -tud;
+            F tud = (float)kTwiceUnskew4 * ( dxS + dyS + dzS + dwS );
+            F xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
+            F xyzwN = -tud;
 
-            float maxScore = 0.6f - xyzwN;
-            i32 bits = 0.2f > maxScore ? -1 : 0;
+            F maxScore = 0.6f - xyzwN;
+            I bits = select( 0.2f > maxScore, I( -1 ), I( 0 ) );
             maxScore = max_( maxScore, 0.2f );
             FN2_CONSIDER( -wN, 7 )
             FN2_CONSIDER( -zN, 11 )
@@ -241,31 +257,31 @@ namespace fn2
             FN2_CONSIDER( zN, 12 )
 #undef FN2_CONSIDER
 
-            bool moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0, moveW = ( bits & 8 ) != 0;
-            xBase = moveX ? xBase + 1.0f : xBase;
-            yBase = moveY ? yBase + 1.0f : yBase;
-            zBase = moveZ ? zBase + 1.0f : zBase;
-            wBase = moveW ? wBase + 1.0f : wBase;
-            dxS = moveX ? dxS - 1.0f : dxS;
-            dyS = moveY ? dyS - 1.0f : dyS;
-            dzS = moveZ ? dzS - 1.0f : dzS;
-            dwS = moveW ? dwS - 1.0f : dwS;
+            B moveX = ( bits & 1 ) != 0, moveY = ( bits & 2 ) != 0, moveZ = ( bits & 4 ) != 0, moveW = ( bits & 8 ) != 0;
+            xBase = select( moveX, xBase + 1.0f, xBase );
+            yBase = select( moveY, yBase + 1.0f, yBase );
+            zBase = select( moveZ, zBase + 1.0f, zBase );
+            wBase = select( moveW, wBase + 1.0f, wBase );
+            dxS = select( moveX, dxS - 1.0f, dxS );
+            dyS = select( moveY, dyS - 1.0f, dyS );
+            dzS = select( moveZ, dzS - 1.0f, dzS );
+            dwS = select( moveW, dwS - 1.0f, dwS );
         }
 
-        i32 xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ ), wP = imul( cvt_i( wBase ), kPW );
+        I xP = imul( cvt_i( xBase ), kPX ), yP = imul( cvt_i( yBase ), kPY ), zP = imul( cvt_i( zBase ), kPZ ), wP = imul( cvt_i( wBase ), kPW );
 
-        float sum = dxS + dyS + dzS + dwS;
-        float tud = (float)kTwiceUnskew4 * sum;
-        float xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
-        float xyzwN = -tud;
+        F sum = dxS + dyS + dzS + dwS;
+        F tud = (float)kTwiceUnskew4 * sum;
+        F xN = dxS + tud, yN = dyS + tud, zN = dzS + tud, wN = dwS + tud;
+        F xyzwN = -tud;
 
-        float ud = (float)kUnskew4 * sum;
-        float dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud, dwB = dwS + ud;
-        float coordSum = (float)( 1 + 4 * kUnskew4 ) * sum;
+        F ud = (float)kUnskew4 * sum;
+        F dxB = dxS + ud, dyB = dyS + ud, dzB = dzS + ud, dwB = dwS + ud;
+        F coordSum = (float)( 1 + 4 * kUnskew4 ) * sum;
 
-        float stemA, stemB;
+        F stemA, stemB;
         { // <0,0,0,0>
-            float fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
+            F fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
             v[0] = { hash_hb( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
@@ -276,15 +292,15 @@ namespace fn2
         // the vertex-class specific falloff base expression [Simplex.inl:692-931].
 #define FN2_SS4_VERTEX( SLOT, COND, MX, MY, MZ, MW, K, FALLOFF ) \
         { \
-            bool sm = COND; \
-            i32 sign = signbit_if( sm ); \
-            float o1 = fxor( (float)( K * kUnskew4 + 1 ), sign ); \
-            float o0 = fxor( (float)( K * kUnskew4 ), sign ); \
+            B sm = COND; \
+            I sign = signbit_if( sm ); \
+            F o1 = fxor( (float)( K * kUnskew4 + 1 ), sign ); \
+            F o0 = fxor( (float)( K * kUnskew4 ), sign ); \
             (void)o0; \
-            float fb = max_( FALLOFF, 0.0f ); \
-            v[SLOT] = { hash_hb( seed, MX ? step_prime( xP, kPX, sm ) : xP, MY ? step_prime( yP, kPY, sm ) : yP, \
-                                     MZ ? step_prime( zP, kPZ, sm ) : zP, MW ? step_prime( wP, kPW, sm ) : wP ), \
-                        dxB - ( MX ? o1 : o0 ), dyB - ( MY ? o1 : o0 ), dzB - ( MZ ? o1 : o0 ), dwB - ( MW ? o1 : o0 ), sq2( fb ) }; \
+            F fb = max_( FALLOFF, 0.0f ); \
+            v[SLOT] = { hash_hb( seed, select( MX, step_prime( xP, kPX, sm ), xP ), select( MY, step_prime( yP, kPY, sm ), yP ), select( \
+                                     MZ, step_prime( zP, kPZ, sm ), zP ), select( MW, step_prime( wP, kPW, sm ), wP )), \
+                        dxB - ( select( MX, o1, o0 )), dyB - ( select( MY, o1, o0 )), dzB - ( select( MZ, o1, o0 )), dwB - ( select( MW, o1, o0 )), sq2( fb ) }; \
         }
 
         FN2_SS4_VERTEX( 1, xyzwN < 0.0f, 1, 1, 1, 1, 4, fma_( o1, coordSum, stemA ) )
@@ -305,11 +321,14 @@ namespace fn2
 #undef FN2_SS4_VERTEX
     }
 
-    FN2_DI float supersimplex4( i32 seed, float x, float y, float z, float w )
+    template<class F>
+    FN2_DI F supersimplex4( i32 seed, F x, F y, F z, F w )
     {
-        Verts4 v[16];
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        Verts4<F> v[16];
         supersimplex4_vertices( seed, x, y, z, w, v );
-        float value = v[0].falloff * grad_dot4( v[0].hb, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
+        F value = v[0].falloff * grad_dot4( v[0].hb, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
 #pragma unroll
         for( int k = 1; k < 16; k++ ) value = fma_( v[k].falloff, grad_dot4( v[k].hb, v[k].dx, v[k].dy, v[k].dz, v[k].dw ), value );
         return value;

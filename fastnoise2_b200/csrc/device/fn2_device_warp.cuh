@@ -8,23 +8,26 @@
 
 namespace fn2
 {
-    FN2_DI float warp_gradient2( i32 seed, float warpAmp, float x, float y, float& xOut, float& yOut, float ax, float ay )
+    template<class F>
+    FN2_DI F warp_gradient2( i32 seed, F warpAmp, F x, F y, F& xOut, F& yOut, float ax, float ay )
     {
-        float xs = floor_( x ), ys = floor_( y );
-        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY );
-        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY );
-        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys );
-        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1;
-        const float normalise = 1.0f / ( 0xffff / 2.0f );
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F xs = floor_( x ), ys = floor_( y );
+        I x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY );
+        I x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY );
+        F xs1 = hermite( x - xs ), ys1 = hermite( y - ys );
+        F xs0 = 1.0f - xs1, ys0 = 1.0f - ys1;
+        const F normalise = 1.0f / ( 0xffff / 2.0f );
 
-        float xWarp, yWarp;
+        F xWarp, yWarp;
         {
-            i32 h = hash_hb( seed, x0, y0 );
-            float c = xs0 * ys0;
+            I h = hash_hb( seed, x0, y0 );
+            F c = xs0 * ys0;
             xWarp = c * field_f<0, 16>( h );
             yWarp = c * cvt_f( lsr( h, 16 ) );
         }
-#define FN2_CORNER( XS, YS, XP, YP ) { i32 h = hash_hb( seed, XP, YP ); float c = XS * YS; \
+#define FN2_CORNER( XS, YS, XP, YP ) { I h = hash_hb( seed, XP, YP ); F c = XS * YS; \
             xWarp = fma_( c, field_f<0, 16>( h ), xWarp ); yWarp = fma_( c, cvt_f( lsr( h, 16 ) ), yWarp ); }
         FN2_CORNER( xs1, ys0, x1, y0 )
         FN2_CORNER( xs0, ys1, x0, y1 )
@@ -38,24 +41,27 @@ namespace fn2
         return fma_( xWarp, xWarp, yWarp * yWarp );
     }
 
-    FN2_DI float warp_gradient3( i32 seed, float warpAmp, float x, float y, float z, float& xOut, float& yOut, float& zOut, float ax, float ay, float az )
+    template<class F>
+    FN2_DI F warp_gradient3( i32 seed, F warpAmp, F x, F y, F z, F& xOut, F& yOut, F& zOut, float ax, float ay, float az )
     {
-        float xs = floor_( x ), ys = floor_( y ), zs = floor_( z );
-        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ );
-        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ );
-        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs );
-        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1;
-        const float normalise = 1.0f / ( 0x3ff / 2.0f );
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F xs = floor_( x ), ys = floor_( y ), zs = floor_( z );
+        I x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ );
+        I x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ );
+        F xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs );
+        F xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1;
+        const F normalise = 1.0f / ( 0x3ff / 2.0f );
 
-        float xWarp, yWarp, zWarp;
+        F xWarp, yWarp, zWarp;
         {
-            i32 h = hash_hb( seed, x0, y0, z0 );
-            float c = xs0 * ys0 * zs0;
+            I h = hash_hb( seed, x0, y0, z0 );
+            F c = xs0 * ys0 * zs0;
             xWarp = c * field_f<0, 10>( h );
             yWarp = c * field_f<11, 10>( h );
             zWarp = c * cvt_f( lsr( h, 22 ) );
         }
-#define FN2_CORNER( XS, YS, ZS, XP, YP, ZP ) { i32 h = hash_hb( seed, XP, YP, ZP ); float c = XS * YS * ZS; \
+#define FN2_CORNER( XS, YS, ZS, XP, YP, ZP ) { I h = hash_hb( seed, XP, YP, ZP ); F c = XS * YS * ZS; \
             xWarp = fma_( c, field_f<0, 10>( h ), xWarp ); yWarp = fma_( c, field_f<11, 10>( h ), yWarp ); zWarp = fma_( c, cvt_f( lsr( h, 22 ) ), zWarp ); }
         FN2_CORNER( xs1, ys0, zs0, x1, y0, z0 )
         FN2_CORNER( xs0, ys1, zs0, x0, y1, z0 )
@@ -75,26 +81,29 @@ namespace fn2
         return fma_( xWarp, xWarp, fma_( yWarp, yWarp, zWarp * zWarp ) );
     }
 
-    FN2_DI float warp_gradient4( i32 seed, float warpAmp, float x, float y, float z, float w,
-                                 float& xOut, float& yOut, float& zOut, float& wOut, float ax, float ay, float az, float aw )
+    template<class F>
+    FN2_DI F warp_gradient4( i32 seed, F warpAmp, F x, F y, F z, F w,
+                                 F& xOut, F& yOut, F& zOut, F& wOut, float ax, float ay, float az, float aw )
     {
-        float xs = floor_( x ), ys = floor_( y ), zs = floor_( z ), ws = floor_( w );
-        i32 x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ ), w0 = imul( cvt_i( ws ), kPW );
-        i32 x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ ), w1 = iadd( w0, kPW );
-        float xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs ), ws1 = hermite( w - ws );
-        float xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1, ws0 = 1.0f - ws1;
-        const float normalise = 1.0f / ( 0xff / 2.0f );
+        typedef typename pack<F>::I I;
+        typedef typename pack<F>::B B;
+        F xs = floor_( x ), ys = floor_( y ), zs = floor_( z ), ws = floor_( w );
+        I x0 = imul( cvt_i( xs ), kPX ), y0 = imul( cvt_i( ys ), kPY ), z0 = imul( cvt_i( zs ), kPZ ), w0 = imul( cvt_i( ws ), kPW );
+        I x1 = iadd( x0, kPX ), y1 = iadd( y0, kPY ), z1 = iadd( z0, kPZ ), w1 = iadd( w0, kPW );
+        F xs1 = hermite( x - xs ), ys1 = hermite( y - ys ), zs1 = hermite( z - zs ), ws1 = hermite( w - ws );
+        F xs0 = 1.0f - xs1, ys0 = 1.0f - ys1, zs0 = 1.0f - zs1, ws0 = 1.0f - ws1;
+        const F normalise = 1.0f / ( 0xff / 2.0f );
 
-        float xWarp, yWarp, zWarp, wWarp;
+        F xWarp, yWarp, zWarp, wWarp;
         {
-            i32 h = hash_hb( seed, x0, y0, z0, w0 );
-            float c = xs0 * ys0 * zs0 * ws0;
+            I h = hash_hb( seed, x0, y0, z0, w0 );
+            F c = xs0 * ys0 * zs0 * ws0;
             xWarp = c * field_f<0, 8>( h );
             yWarp = c * field_f<8, 8>( h );
             zWarp = c * cvt_f( ( h >> 16 ) & 0xff );
             wWarp = c * cvt_f( lsr( h, 24 ) );
         }
-#define FN2_CORNER( XS, YS, ZS, WS, XP, YP, ZP, WP ) { i32 h = hash_hb( seed, XP, YP, ZP, WP ); float c = XS * YS * ZS * WS; \
+#define FN2_CORNER( XS, YS, ZS, WS, XP, YP, ZP, WP ) { I h = hash_hb( seed, XP, YP, ZP, WP ); F c = XS * YS * ZS * WS; \
             xWarp = fma_( c, field_f<0, 8>( h ), xWarp ); yWarp = fma_( c, field_f<8, 8>( h ), yWarp ); \
             zWarp = fma_( c, cvt_f( ( h >> 16 ) & 0xff ), zWarp ); wWarp = fma_( c, cvt_f( lsr( h, 24 ) ), wWarp ); }
         FN2_CORNER( xs1, ys0, zs0, ws0, x1, y0, z0, w0 )

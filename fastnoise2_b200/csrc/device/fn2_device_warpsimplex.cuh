@@ -11,8 +11,6 @@
 
 namespace fn2
 {
-    FN2_DI float sel_hi( i32 selector, float a, float b ) { return selector < 0 ? a : b; } // FS::SelectHighBit
-
     constexpr float kSkew2f = (float)( 1.0 / ( kRoot3 + 1.0 ) );
     constexpr float kSkew4f = (float)( 1.0 / ( kRoot5 + 1.0 ) );
     constexpr float kRoot2f = (float)kRoot2;
@@ -297,14 +295,14 @@ namespace fn2
         float valueX = 0.0f, valueY = 0.0f;
         if( LATTICE == 0 )
         {
-            Verts2 v[3];
+            Verts2<float> v[3];
             simplex2_vertices( seed, x, y, v );
 #pragma unroll
             for( int k = 0; k < 3; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
         }
         else
         {
-            Verts2 v[4];
+            Verts2<float> v[4];
             supersimplex2_vertices( seed, x, y, v );
 #pragma unroll
             for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
@@ -322,14 +320,14 @@ namespace fn2
         float valueX = 0.0f, valueY = 0.0f, valueZ = 0.0f;
         if( LATTICE == 0 )
         {
-            Verts3 v[4];
+            Verts3<float> v[4];
             simplex3_vertices( seed, x, y, z, v );
 #pragma unroll
             for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
         }
         else
         {
-            Verts3 v[8];
+            Verts3<float> v[8];
             supersimplex3_vertices( seed, x, y, z, v );
 #pragma unroll
             for( int k = 0; k < 8; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
@@ -358,14 +356,14 @@ namespace fn2
         float valueX = 0.0f, valueY = 0.0f, valueZ = 0.0f, valueW = 0.0f;
         if( LATTICE == 0 )
         {
-            Verts4 v[5];
+            Verts4<float> v[5];
             simplex4_vertices( seed, x, y, z, w, v );
 #pragma unroll
             for( int k = 0; k < 5; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
         }
         else
         {
-            Verts4 v[16];
+            Verts4<float> v[16];
             supersimplex4_vertices( seed, x, y, z, w, v );
 #pragma unroll
             for( int k = 0; k < 16; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
@@ -379,5 +377,32 @@ namespace fn2
         zOut = fma_( valueZ, warpAmp, zOut );
         wOut = fma_( valueW, warpAmp, wOut );
         return fma_( valueW, valueW, fma_( valueZ, valueZ, fma_( valueY, valueY, valueX * valueX ) ) );
+    }
+
+    // pack forms, lane by lane: the vector contributions are index arithmetic and selects almost throughout
+    template<int LATTICE, int SCHEME>
+    FN2_DI fpair warp_simplex2( i32 seed, fpair warpAmp, fpair x, fpair y, fpair& xOut, fpair& yOut, float boundAx, float boundAy )
+    {
+        fpair r;
+        r.x = warp_simplex2<LATTICE, SCHEME>( seed, warpAmp.x, x.x, y.x, xOut.x, yOut.x, boundAx, boundAy );
+        r.y = warp_simplex2<LATTICE, SCHEME>( seed, warpAmp.y, x.y, y.y, xOut.y, yOut.y, boundAx, boundAy );
+        return r;
+    }
+    template<int LATTICE, int SCHEME>
+    FN2_DI fpair warp_simplex3( i32 seed, fpair warpAmp, fpair x, fpair y, fpair z, fpair& xOut, fpair& yOut, fpair& zOut, float boundAx, float boundAy, float boundAz )
+    {
+        fpair r;
+        r.x = warp_simplex3<LATTICE, SCHEME>( seed, warpAmp.x, x.x, y.x, z.x, xOut.x, yOut.x, zOut.x, boundAx, boundAy, boundAz );
+        r.y = warp_simplex3<LATTICE, SCHEME>( seed, warpAmp.y, x.y, y.y, z.y, xOut.y, yOut.y, zOut.y, boundAx, boundAy, boundAz );
+        return r;
+    }
+    template<int LATTICE, int SCHEME>
+    FN2_DI fpair warp_simplex4( i32 seed, fpair warpAmp, fpair x, fpair y, fpair z, fpair w, fpair& xOut, fpair& yOut, fpair& zOut, fpair& wOut,
+                                float boundAx, float boundAy, float boundAz, float boundAw )
+    {
+        fpair r;
+        r.x = warp_simplex4<LATTICE, SCHEME>( seed, warpAmp.x, x.x, y.x, z.x, w.x, xOut.x, yOut.x, zOut.x, wOut.x, boundAx, boundAy, boundAz, boundAw );
+        r.y = warp_simplex4<LATTICE, SCHEME>( seed, warpAmp.y, x.y, y.y, z.y, w.y, xOut.y, yOut.y, zOut.y, wOut.y, boundAx, boundAy, boundAz, boundAw );
+        return r;
     }
 }

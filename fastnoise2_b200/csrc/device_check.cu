@@ -15,6 +15,9 @@ namespace
         __device__ float operator()( float, float ) const { return p; }
         __device__ float operator()( float, float, float ) const { return p; }
         __device__ float operator()( float, float, float, float ) const { return p; }
+        __device__ fn2::fpair operator()( fn2::fpair, fn2::fpair ) const { return p; }
+        __device__ fn2::fpair operator()( fn2::fpair, fn2::fpair, fn2::fpair ) const { return p; }
+        __device__ fn2::fpair operator()( fn2::fpair, fn2::fpair, fn2::fpair, fn2::fpair ) const { return p; }
     };
 }
 
@@ -58,6 +61,49 @@ extern "C" __global__ void __launch_bounds__( 256 ) fn2_device_check( float* __r
     out[i] = v;
 }
 
+// the same leaves through the two-points-per-value (packed FP32) instantiations; thread i evaluates points 2i and 2i+1 at ( i*step, i*step*0.7, i*step*0.3, i*step*0.1 )
+extern "C" __global__ void __launch_bounds__( 256 ) fn2_device_check_pair( float* __restrict__ out, int n, int which, int seed, float step )
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    fn2::stage_tables();
+    if( 2 * i + 1 >= n ) return;
+    const float xa = ( 2 * i ) * step, xb = ( 2 * i + 1 ) * step;
+    const fn2::fpair x( xa, xb ), y( xa * 0.7f, xb * 0.7f ), z( xa * 0.3f, xb * 0.3f ), w( xa * 0.1f, xb * 0.1f );
+    fn2::fpair v = 0.0f;
+    fn2::fpair d[4];
+    fn2::fpair cx, cy, cz, cw;
+    switch( which )
+    {
+    case 0: v = fn2::simplex2( seed, x, y ); break;
+    case 1: v = fn2::simplex3( seed, x, y, z ); break;
+    case 2: v = fn2::simplex4( seed, x, y, z, w ); break;
+    case 3: v = fn2::supersimplex2( seed, x, y ); break;
+    case 4: v = fn2::supersimplex3( seed, x, y, z ); break;
+    case 5: v = fn2::supersimplex4( seed, x, y, z, w ); break;
+    case 6: v = fn2::perlin2( seed, x, y ); break;
+    case 7: v = fn2::perlin3( seed, x, y, z ); break;
+    case 8: v = fn2::perlin4( seed, x, y, z, w ); break;
+    case 9: v = fn2::value2( seed, x, y ) + fn2::value3( seed, x, y, z ) + fn2::value4( seed, x, y, z, w ); break;
+    case 10: v = fn2::white( seed, x, y ) + fn2::white( seed, x, y, z ) + fn2::white( seed, x, y, z, w ); break;
+    case 11: fn2::cellular_distance2<1, false, 1>( seed, x, y, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f }, d ); v = d[0] + d[1]; break;
+    case 12: fn2::cellular_distance3<1, false, 0>( seed, x, y, z, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f }, d ); v = d[0]; break;
+    case 13: fn2::cellular_distance4<5, true, 3>( seed, x, y, z, w, fn2::fpair( 0.4f ), fn2::fpair( 0.001f ), ConstP { 1.5f }, d ); v = d[3]; break;
+    case 14: v = fn2::cvt_f( fn2::cellular_value2<0, false, 0>( seed, x, y, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f } ) ); break;
+    case 15: v = fn2::cvt_f( fn2::cellular_value3<2, true, 2>( seed, x, y, z, fn2::fpair( 0.4f ), fn2::fpair( 0.001f ), ConstP { 1.5f } ) ); break;
+    case 16: v = fn2::cvt_f( fn2::cellular_value4<3, false, 1>( seed, x, y, z, w, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f } ) ); break;
+    case 17: fn2::cellular_lookup2<1, false>( seed, x, y, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f }, cx, cy ); v = cx + cy; break;
+    case 18: fn2::cellular_lookup3<1, false>( seed, x, y, z, fn2::fpair( 0.4f ), fn2::fpair( 0.0f ), ConstP { 1.5f }, cx, cy, cz ); v = cx + cy + cz; break;
+    case 19: fn2::cellular_lookup4<4, true>( seed, x, y, z, w, fn2::fpair( 0.4f ), fn2::fpair( 0.001f ), ConstP { 1.5f }, cx, cy, cz, cw ); v = cx + cy + cz + cw; break;
+    case 20: { fn2::fpair a = x, b = y; v = fn2::warp_gradient2( seed, fn2::fpair( 30.f ), x * 0.01f, y * 0.01f, a, b, 1.f, 1.f ) + a + b; break; }
+    case 21: { fn2::fpair a = x, b = y, c = z; v = fn2::warp_gradient3( seed, fn2::fpair( 30.f ), x * 0.01f, y * 0.01f, z * 0.01f, a, b, c, 1.f, 1.f, 1.f ) + a + b + c; break; }
+    case 22: { fn2::fpair a = x, b = y, c = z, e = w; v = fn2::warp_gradient4( seed, fn2::fpair( 30.f ), x * 0.01f, y * 0.01f, z * 0.01f, w * 0.01f, a, b, c, e, 1.f, 1.f, 1.f, 1.f ) + a + b + c + e; break; }
+    case 23: v = fn2::sinewave( x, y, z, w ) + fn2::checkerboard( x, y, z ) + fn2::pow_pos( fn2::abs_( x ) + 0.5f, 1.5f ) + fn2::modulus( x, 3.0f ); break;
+    }
+    out[2 * i] = v.x;
+    out[2 * i + 1] = v.y;
+}
+
+
 // Exhaustive equality of the check-free Newton sequence with the IEEE intrinsics over a range of float bit patterns.
 extern "C" __global__ void __launch_bounds__( 256 ) fn2_selftest_inv_sqrt( unsigned firstBits, unsigned count, unsigned long long* __restrict__ mismatches )
 {
@@ -75,6 +121,20 @@ namespace FastNoise
 {
     namespace Impl
     {
+        // Runs leaf `which` of the device library over n points (one point per value, or two with packed FP32) into hostOut.
+        int SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut )
+        {
+            if( n <= 0 || ( n & 1 ) || !hostOut ) return -1;
+            float* dev = nullptr;
+            if( cudaMalloc( &dev, (size_t)n * sizeof( float ) ) != cudaSuccess ) return -2;
+            cudaMemset( dev, 0, (size_t)n * sizeof( float ) );
+            if( packed ) fn2_device_check_pair<<<( n / 2 + 255 ) / 256, 256>>>( dev, n, which, seed, step );
+            else fn2_device_check<<<( n + 255 ) / 256, 256>>>( dev, n, which, seed, step );
+            const cudaError_t e = cudaMemcpy( hostOut, dev, (size_t)n * sizeof( float ), cudaMemcpyDeviceToHost );
+            cudaFree( dev );
+            return e == cudaSuccess ? 0 : -3;
+        }
+
         // 0 = every value agrees; > 0 = mismatch count; < 0 = CUDA error
         long long SelfTestInvSqrt( float lo, float hi )
         {

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -69,8 +70,8 @@ namespace
         return s;
     }
 
-    // "float x, float y, float z"
-    std::string PosDecl( int dim, const char* type = "float ", const char* prefix = "" )
+    // "F x, F y, F z" -- F is float or fn2::fpair, see the typedefs LowerTree emits
+    std::string PosDecl( int dim, const char* type = "F ", const char* prefix = "" )
     {
         std::string s;
         for( int d = 0; d < dim; d++ )
@@ -124,7 +125,7 @@ namespace
                 {
                     std::string body = Body( g, k, dim ); // emits the children first
                     out << "// " << g->GetMetadata().name << " " << dim << "D\n"
-                        << "FN2_DI float n" << k << "_" << dim << "( int seed, " << PosDecl( dim ) << " )\n{\n" << body << "}\n\n";
+                        << "FN2_DI F n" << k << "_" << dim << "( int seed, " << PosDecl( dim ) << " )\n{\n" << body << "}\n\n";
                 }
                 --depth;
             }
@@ -187,7 +188,7 @@ namespace
 
             const Impl::NodeState& s = g->State();
             out << "// " << g->GetMetadata().name << "::Warp " << dim << "D\n"
-                << "FN2_DI float " << name << "( int seed, float warpAmp, " << PosDecl( dim, "float ", "s" ) << ", " << PosDecl( dim, "float& " ) << " )\n{\n";
+                << "FN2_DI F " << name << "( int seed, F warpAmp, " << PosDecl( dim, "F ", "s" ) << ", " << PosDecl( dim, "F& " ) << " )\n{\n";
             if( s.nodeId == N_DomainWarpGradient )
             {
                 out << AddSeedOffset( s ) // Warp() adds the offset itself [DomainWarp.inl:35,79,136]
@@ -243,12 +244,12 @@ namespace
                 const char* sizeK = dim == 2 ? "fn2::kSizeJitterScale2D" : ( dim == 3 ? "fn2::kSizeJitterScale3D" : "fn2::kSizeJitterScale4D" );
                 bool sizeJ = s.hybrids[2].node || s.hybrids[2].constant != 0.0f;
                 b << "    const int sourceSeed = seed;\n" << AddSeedOffset( s );
-                b << "    const float jitter = " << jitterK << " * " << Hyb( g, 1, dim, "sourceSeed", P ) << ";\n";
-                if( sizeJ ) b << "    const float sizeJitter = " << Hyb( g, 2, dim, "sourceSeed", P ) << " * " << sizeK << ";\n";
-                else b << "    const float sizeJitter = 0.0f;\n";
+                b << "    const F jitter = " << jitterK << " * " << Hyb( g, 1, dim, "sourceSeed", P ) << ";\n";
+                if( sizeJ ) b << "    const F sizeJitter = " << Hyb( g, 2, dim, "sourceSeed", P ) << " * " << sizeK << ";\n";
+                else b << "    const F sizeJitter = 0.0f;\n";
                 b << ScalePositions( s, dim );
                 // Minkowski exponent is sampled AT the cell delta vector [Utils.inl:330]
-                b << "    auto minkowskiP = [=]( " << PosDecl( dim, "float ", "d" ) << " ) { return " << Hyb( g, 0, dim, "sourceSeed", Pos( dim, "d" ) ) << "; };\n";
+                b << "    auto minkowskiP = [=]( " << PosDecl( dim, "F ", "d" ) << " ) -> F { return " << Hyb( g, 0, dim, "sourceSeed", Pos( dim, "d" ) ) << "; };\n";
                 return sizeJ;
             };
 
@@ -271,7 +272,7 @@ namespace
                 break;
 
             case N_Gradient: // [BasicGenerators.inl:98-108]
-                b << "    float r = 0.0f;\n";
+                b << "    F r = 0.0f;\n";
                 for( int d = 0; d < dim; d++ )
                 {
                     b << "    r = fn2::fma_( " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ", " << Lit( s.f[F_K0 + d] ) << ", r );\n";
@@ -282,11 +283,11 @@ namespace
             case N_DistanceToPoint: // [BasicGenerators.inl:115-125]
             {
                 std::string O = Pos( dim, "o" );
-                for( int d = 0; d < dim; d++ ) b << "    const float o" << kAxis[d] << " = " << kAxis[d] << ";\n";
+                for( int d = 0; d < dim; d++ ) b << "    const F o" << kAxis[d] << " = " << kAxis[d] << ";\n";
                 for( int d = 0; d < dim; d++ ) b << "    " << kAxis[d] << " -= " << Hyb( g, d, dim, "seed", O ) << ";\n";
                 int df = s.i[I_K0];
                 if( df < 0 || df > 5 ) df = 0; // `default:` label of the switch [Utils.inl:286]
-                b << "    return fn2::calc_distance<" << df << ", true>( " << ( df == 5 ? Hyb( g, 4, dim, "seed", P ) : "0.0f" ) << ", " << P << " );\n";
+                b << "    return fn2::calc_distance<" << df << ", true>( F( " << ( df == 5 ? Hyb( g, 4, dim, "seed", P ) : "0.0f" ) << " ), " << P << " );\n";
                 break;
             }
 
@@ -315,7 +316,7 @@ namespace
                 int df = s.i[I_K0];
                 if( df < 0 || df > 5 ) df = 0;
                 int top = s.i[I_K0 + 1];
-                b << "    const int cellHash = fn2::cellular_value" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
+                b << "    const I cellHash = fn2::cellular_value" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
                   << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP );\n";
                 b << "    return " << Range( s, "fn2::cvt_f( cellHash )", -2147483648.f, 2147483648.f ) << ";\n";
                 break;
@@ -329,7 +330,7 @@ namespace
                 int i0 = s.i[I_K0 + 1], i1 = s.i[I_K0 + 2], ret = s.i[I_K0 + 3];
                 if( ret < 0 || ret > 4 ) ret = 0;
                 int top = ( df == 0 || ret != 0 ) ? std::max( i0, i1 ) : i0;
-                b << "    float dist[4];\n";
+                b << "    F dist[4];\n";
                 b << "    fn2::cellular_distance" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
                   << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, dist );\n";
                 if( df == 0 ) // GetReturn [Cellular.inl:533-537]; with index0 == index1 the entry is normalised twice, as there
@@ -358,7 +359,7 @@ namespace
                 int df = s.i[I_K0];
                 if( df < 0 || df > 5 ) df = 0;
                 std::string C = Pos( dim, "c" );
-                b << "    float " << C << ";\n";
+                b << "    F " << C << ";\n";
                 b << "    fn2::cellular_lookup" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, " << C << " );\n";
                 b << "    return " << Src( g, 0, dim, "fn2::iadd( sourceSeed, 1 )", Scaled( dim, Lit( s.f[F_Scale] ), "c" ) ) << ";\n";
                 break;
@@ -372,11 +373,11 @@ namespace
                 int octaves = s.i[I_K0];
                 std::string sample = Src( g, 0, dim, "seed", P );
                 if( ridged ) sample = "fn2::abs_( " + sample + " )";
-                b << "    const float gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                if( weighted ) b << "    const float weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    float amp = 1.0f;\n";
-                b << "    float noise = " << sample << ";\n";
-                b << "    float sum = " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
+                b << "    const F gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                if( weighted ) b << "    const F weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    F amp = 1.0f;\n";
+                b << "    F noise = " << sample << ";\n";
+                b << "    F sum = " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
                 if( octaves > 1 )
                 {
                     b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
@@ -394,10 +395,10 @@ namespace
             }
 
             case N_PingPong: // [Modifiers.inl:185-201]
-                b << "    const float strength = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                b << "    float t = " << Src( g, 0, dim, "seed", P ) << " * strength;\n";
+                b << "    const F strength = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    F t = " << Src( g, 0, dim, "seed", P ) << " * strength;\n";
                 b << "    t -= fn2::floor_( t * 0.5f ) * 2.0f;\n";
-                b << "    return t < 1.0f ? t : 2.0f - t;\n";
+                b << "    return fn2::select( t < 1.0f, t, 2.0f - t );\n";
                 break;
 
             case N_DomainWarpSimplex:
@@ -406,7 +407,7 @@ namespace
             {
                 std::string warp = Warp( g, dim );
                 b << "    const int sourceSeed = seed;\n" << AddSeedOffset( s );
-                b << "    const float warpAmp = " << Hyb( g, 0, dim, "sourceSeed", P ) << ";\n";
+                b << "    const F warpAmp = " << Hyb( g, 0, dim, "sourceSeed", P ) << ";\n";
                 b << "    " << warp << "( seed, warpAmp, " << Scaled( dim, Lit( s.f[F_Frequency] ) ) << ", " << P << " );\n";
                 b << "    return " << Src( g, 0, dim, "sourceSeed", P ) << ";\n";
                 break;
@@ -428,13 +429,13 @@ namespace
                 int octaves = s.i[I_K0];
                 std::string warp = Warp( warpNode, dim );
                 std::string N = independent ? Pos( dim, "n" ) : P; // position the frequency is applied to
-                b << "    float amp = " << Hyb( warpNode, 0, dim, "seed", P ) << ";\n";
-                if( weighted ) b << "    const float weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    float freq = " << Lit( ws.f[F_Frequency] ) << ";\n";
+                b << "    F amp = " << Hyb( warpNode, 0, dim, "seed", P ) << ";\n";
+                if( weighted ) b << "    const F weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    F freq = " << Lit( ws.f[F_Frequency] ) << ";\n";
                 b << "    int seedInc = seed;\n";
-                b << "    const float gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                if( independent ) for( int d = 0; d < dim; d++ ) b << "    const float n" << kAxis[d] << " = " << kAxis[d] << ";\n";
-                b << "    float strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
+                b << "    const F gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                if( independent ) for( int d = 0; d < dim; d++ ) b << "    const F n" << kAxis[d] << " = " << kAxis[d] << ";\n";
+                b << "    F strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
                 if( octaves > 1 )
                 {
                     b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
@@ -478,7 +479,7 @@ namespace
                 break;
 
             case N_SignedSquareRoot: // [Modifiers.inl:324-335]
-                b << "    const float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F v = " << Src( g, 0, dim, "seed", P ) << ";\n";
                 b << "    return fn2::bitsf( fn2::fbits( fn2::fast_length_sqrt( fn2::abs_( v ) ) ) | ( fn2::fbits( v ) & (int)0x80000000u ) );\n";
                 break;
 
@@ -486,23 +487,23 @@ namespace
             case N_MaxSmooth: // [Blends.inl:145-162]
             {
                 const char* neg = s.nodeId == N_MaxSmooth ? "-" : "";
-                b << "    const float a = " << neg << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const float b = " << neg << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const float smoothness = fn2::max_( 0x1p-126f, fn2::abs_( " << Hyb( g, 1, dim, "seed", P ) << " ) );\n";
-                b << "    float h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
+                b << "    const F a = " << neg << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F b = " << neg << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F smoothness = fn2::max_( 0x1p-126f, fn2::abs_( " << Hyb( g, 1, dim, "seed", P ) << " ) );\n";
+                b << "    F h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
                 b << "    h *= fn2::reciprocal( smoothness );\n";
                 b << "    return " << neg << "fn2::fnma_( " << Lit( 1.0f / 6.0f ) << ", h * h * h * smoothness, fn2::min_( a, b ) );\n";
                 break;
             }
 
             case N_PowFloat: // [Blends.inl:72-82]
-                b << "    const float v = fn2::max_( fn2::abs_( " << Hyb( g, 0, dim, "seed", P ) << " ), 0x1p-126f );\n";
+                b << "    const F v = fn2::max_( fn2::abs_( " << Hyb( g, 0, dim, "seed", P ) << " ), 0x1p-126f );\n";
                 b << "    return fn2::pow_pos( v, " << Hyb( g, 1, dim, "seed", P ) << " );\n";
                 break;
 
             case N_PowInt: // [Blends.inl:84-101]
-                b << "    const float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    float p = v * v;\n";
+                b << "    const F v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    F p = v * v;\n";
                 b << "    for( int i = 2; i < " << Int( s.i[I_K0] ) << "; i++ ) p *= v;\n";
                 b << "    return p;\n";
                 break;
@@ -514,7 +515,7 @@ namespace
             case N_DomainOffset: // [Modifiers.inl:15-28] every offset is sampled at the un-offset position
             {
                 std::string O = Pos( dim, "o" );
-                for( int d = 0; d < dim; d++ ) b << "    const float o" << kAxis[d] << " = " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ";\n";
+                for( int d = 0; d < dim; d++ ) b << "    const F o" << kAxis[d] << " = " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ";\n";
                 b << "    return " << Src( g, 0, dim, "seed", O ) << ";\n";
                 break;
             }
@@ -561,12 +562,12 @@ namespace
             case N_ConvertRGBA8: // [Modifiers.inl:103-127]
             {
                 const float lo = s.f[F_K0], hi = s.f[F_K0 + 1];
-                b << "    float v = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    F v = " << Src( g, 0, dim, "seed", P ) << ";\n";
                 b << "    v = fn2::min_( v, " << Lit( hi ) << " );\n";
                 b << "    v = fn2::max_( v, " << Lit( lo ) << " );\n";
                 b << "    v -= " << Lit( lo ) << ";\n";
                 b << "    v *= " << Lit( 255.0f / ( hi - lo ) ) << ";\n";
-                b << "    const int byteVal = fn2::cvt_i( v );\n";
+                b << "    const I byteVal = fn2::cvt_i( v );\n";
                 b << "    return fn2::bitsf( (int)0xff000000u | byteVal | fn2::shl( byteVal, 8 ) | fn2::shl( byteVal, 16 ) );\n";
                 break;
             }
@@ -577,26 +578,26 @@ namespace
 
             case N_Fade: // [Blends.inl:164-199]
             {
-                b << "    float fade = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const float fadeMin = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    const float fadeMax = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
-                b << "    const float fadeRange = fadeMax - fadeMin;\n";
+                b << "    F fade = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F fadeMin = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    const F fadeMax = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
+                b << "    const F fadeRange = fadeMax - fadeMin;\n";
                 b << "    fade = fn2::div_( fade - fadeMin, fadeRange );\n";
                 b << "    fade = fn2::max_( 0.0f, fn2::min_( 1.0f, fade ) );\n";
                 if( s.i[I_K0] == 1 ) b << "    fade = fn2::hermite( fade );\n";
                 if( s.i[I_K0] == 2 ) b << "    fade = fn2::quintic( fade );\n";
-                b << "    fade = fadeRange == 0.0f ? 0.5f : fade;\n";
+                b << "    fade = fn2::select( fadeRange == 0.0f, F( 0.5f ), fade );\n";
                 b << "    return fn2::lerp( " << Src( g, 0, dim, "seed", P ) << ", " << Src( g, 1, dim, "seed", P ) << ", fade );\n";
                 break;
             }
 
             case N_Remap: // [Modifiers.inl:76-100]
-                b << "    const float source = " << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const float fromMin = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const float fromMax = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    const float toMin = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
-                b << "    const float toMax = " << Hyb( g, 3, dim, "seed", P ) << ";\n";
-                b << "    float result = toMin + ( fn2::div_( source - fromMin, fromMax - fromMin ) * ( toMax - toMin ) );\n";
+                b << "    const F source = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F fromMin = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                b << "    const F fromMax = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
+                b << "    const F toMin = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
+                b << "    const F toMax = " << Hyb( g, 3, dim, "seed", P ) << ";\n";
+                b << "    F result = toMin + ( fn2::div_( source - fromMin, fromMax - fromMin ) * ( toMax - toMin ) );\n";
                 if( s.i[I_K0] == 1 )
                 {
                     b << "    result = fn2::max_( result, toMin );\n";
@@ -607,22 +608,22 @@ namespace
 
             case N_Terrace: // [Modifiers.inl:130-182]
             {
-                b << "    float source = " << Src( g, 0, dim, "seed", P ) << ";\n";
+                b << "    F source = " << Src( g, 0, dim, "seed", P ) << ";\n";
                 b << "    source *= " << Lit( s.f[F_K0] ) << ";\n";
-                b << "    float rounded = fn2::round_( source );\n";
+                b << "    F rounded = fn2::round_( source );\n";
                 const bool dynamic = (bool)s.hybrids[0].node;
                 if( dynamic || s.hybrids[0].constant != 0.0f )
                 {
-                    if( dynamic ) b << "    const float smoothness = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                    b << "    float diff = rounded - source;\n";
-                    b << "    const bool diffSign = diff < 0.0f;\n";
+                    if( dynamic ) b << "    const F smoothness = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
+                    b << "    F diff = rounded - source;\n";
+                    b << "    const B diffSign = diff < 0.0f;\n";
                     b << "    diff = fn2::abs_( diff );\n";
                     b << "    diff = 0.5f - diff;\n";
                     if( dynamic ) b << "    diff *= 1.0f + fn2::reciprocal( smoothness );\n";
                     else b << "    diff *= " << Lit( s.f[F_K0 + 2] ) << ";\n";
                     b << "    diff = fn2::min_( diff, 0.5f );\n";
-                    b << "    diff = diffSign ? 0.5f - diff : diff - 0.5f;\n";
-                    if( dynamic ) b << "    rounded = smoothness != 0.0f ? rounded + diff : rounded;\n";
+                    b << "    diff = fn2::select( diffSign, 0.5f - diff, diff - 0.5f );\n";
+                    if( dynamic ) b << "    rounded = fn2::select( smoothness != 0.0f, rounded + diff, rounded );\n";
                     else b << "    rounded += diff;\n";
                 }
                 b << "    return rounded * " << Lit( s.f[F_K0 + 1] ) << ";\n";
@@ -658,14 +659,14 @@ namespace
             case N_DomainRotatePlane: // [Modifiers.inl:352-409]
             {
                 bool xz = dim != 2 && s.i[I_K0] == 1; // 2D input always uses the XY preset
-                if( dim == 2 ) b << "    const float z = 0.0f;\n";
+                if( dim == 2 ) b << "    const F z = 0.0f;\n";
                 const char* A = xz ? "z" : "y"; // the axis paired with x
                 const char* B = xz ? "y" : "z"; // the axis that is "improved away"
-                b << "    const float pair = x + " << A << ";\n";
-                b << "    const float s2 = pair * -0.211324865405187f;\n";
-                b << "    float nb = " << B << " * 0.577350269189626f;\n";
-                b << "    const float nx = x + s2 - nb;\n";
-                b << "    const float na = " << A << " + s2 - nb;\n";
+                b << "    const F pair = x + " << A << ";\n";
+                b << "    const F s2 = pair * -0.211324865405187f;\n";
+                b << "    F nb = " << B << " * 0.577350269189626f;\n";
+                b << "    const F nx = x + s2 - nb;\n";
+                b << "    const F na = " << A << " + s2 - nb;\n";
                 b << "    nb = nb + pair * 0.577350269189626f;\n";
                 std::string rotated = xz ? "nx, nb, na" : "nx, na, nb";
                 if( dim == 4 ) rotated += ", w";
@@ -683,10 +684,12 @@ namespace
     };
 
     // ------------------------------------------------------------------ entry kernels
+    // Entry kernels. A thread owns `ppt` consecutive points and evaluates them FN2_W at a time (FN2_W = 2: one fpair per two
+    // points, see fn2_device_pack.cuh); fn2::index_positions / lane_values / spill_lanes are the width-generic glue.
     std::string GridEntry( int dim, const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::GridArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::GridArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
           << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.total;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
@@ -714,13 +717,16 @@ namespace
         // positions exactly as Generator.inl:160-162: fma( float(index), step, offset )
         for( int d = 1; d < dim; d++ )
         {
-            k << "        const float p" << kAxis[d] << " = fn2::fma_( fn2::cvt_f( (int)i" << kAxis[d] << " ), a.step[" << d << "], a.off[" << d << "] );\n";
+            k << "        const F p" << kAxis[d] << " = fn2::fma_( fn2::cvt_f( (int)i" << kAxis[d] << " ), a.step[" << d << "], a.off[" << d << "] );\n";
         }
         k << "        float v[" << ppt << "];\n"
           << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p += FN2_W )\n        {\n"
+          << "            const F px = fn2::index_positions<F>( ix + p, a.step[0], a.off[0] );\n"
+          << "            fn2::spill_lanes( " << root << "( seed, " << Pos( dim, "p" ) << " ), v + p );\n"
+          << "        }\n"
+          << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            const float px = fn2::fma_( fn2::cvt_f( (int)( ix + p ) ), a.step[0], a.off[0] );\n"
-          << "            v[p] = " << root << "( seed, " << Pos( dim, "p" ) << " );\n"
           << "            vmin = fn2::min_( vmin, v[p] );\n"
           << "            vmax = fn2::max_( vmax, v[p] );\n"
           << "        }\n"
@@ -733,7 +739,7 @@ namespace
     std::string TileEntry( const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::TileArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::TileArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
           << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.total;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
@@ -744,15 +750,18 @@ namespace
           << "        const unsigned iy = rowLocal + a.rowBegin;\n"
           // torus mapping [Generator.inl:400-406]
           << "        const float yF = fn2::cvt_f( (int)iy ) * a.yMul;\n"
-          << "        const float py = fn2::cos_poly( yF ) * a.yFreq;\n"
-          << "        const float pw = fn2::sin_poly( yF ) * a.yFreq;\n"
+          << "        const F py = fn2::cos_poly( yF ) * a.yFreq;\n"
+          << "        const F pw = fn2::sin_poly( yF ) * a.yFreq;\n"
           << "        float v[" << ppt << "];\n"
           << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p += FN2_W )\n        {\n"
+          << "            const F xF = fn2::index_positions<F>( ix + p, a.xMul );\n"
+          << "            const F px = fn2::cos_poly( xF ) * a.xFreq;\n"
+          << "            const F pz = fn2::sin_poly( xF ) * a.xFreq;\n"
+          << "            fn2::spill_lanes( " << root << "( seed, px, py, pz, pw ), v + p );\n"
+          << "        }\n"
+          << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            const float xF = fn2::cvt_f( (int)( ix + p ) ) * a.xMul;\n"
-          << "            const float px = fn2::cos_poly( xF ) * a.xFreq;\n"
-          << "            const float pz = fn2::sin_poly( xF ) * a.xFreq;\n"
-          << "            v[p] = " << root << "( seed, px, py, pz, pw );\n"
           << "            vmin = fn2::min_( vmin, v[p] );\n"
           << "            vmax = fn2::max_( vmax, v[p] );\n"
           << "        }\n"
@@ -765,7 +774,7 @@ namespace
     std::string PositionsEntry( int dim, const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK ) fn2_entry( float* __restrict__ out, const fn2::PosArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::PosArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
           << "    const unsigned long long first = ( (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
           << "    const bool valid = first < a.count;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
@@ -790,15 +799,18 @@ namespace
         for( int d = 0; d < dim; d++ ) k << "                in[" << d << "][p] = a.pos[" << d << "][i];\n";
         k << "            }\n        }\n"
           << "#pragma unroll\n"
-          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n";
+          << "        for( int p = 0; p < " << ppt << "; p += FN2_W )\n        {\n";
         // pos = offset + array value [Generator.inl:327-330]
         std::string args;
         for( int d = 0; d < dim; d++ )
         {
             if( d ) args += ", ";
-            args += "a.off[" + std::to_string( d ) + "] + in[" + std::to_string( d ) + "][p]";
+            args += "a.off[" + std::to_string( d ) + "] + fn2::lane_values<F>( in[" + std::to_string( d ) + "] + p )";
         }
-        k << "            v[p] = " << root << "( seed, " << args << " );\n"
+        k << "            fn2::spill_lanes( " << root << "( seed, " << args << " ), v + p );\n"
+          << "        }\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
           << "            if( first + p < a.count )\n            {\n"
           << "                vmin = fn2::min_( vmin, v[p] );\n"
           << "                vmax = fn2::max_( vmax, v[p] );\n"
@@ -838,14 +850,27 @@ namespace FastNoise
                 return program;
             }
 
+            // Two points per value (packed FP32) or one? Packing removes ~20 % of the issued instructions, but a value then takes
+            // a register pair and the kernels end up at 100-250 registers. Measured on B200: a gain for trees
+            // evaluated in 3D (C1 +3 %, C3a +4 %, C4 +3 %), a wash in 2D, a loss in 4D where the lattice functions already
+            // need ~100 registers one point at a time. FASTNOISE2_B200_PACK=0/1 forces it off/on.
+            const int entryDim = entryKind == kTileable2D ? 4 : ( entryKind >= 10 ? entryKind - 10 : entryKind );
+            const char* packEnv = std::getenv( "FASTNOISE2_B200_PACK" );
+            const bool pack = packEnv && *packEnv ? std::atoi( packEnv ) != 0 : entryDim == 3;
+            const int width = pointsPerThread >= 2 && pack ? 2 : 1;
+
             std::ostringstream src;
             src << "// generated by fastnoise2_b200 -- entry kind " << entryKind << ", " << pointsPerThread << " point(s) per thread, "
                 << ( ( mathMode & 1 ) ? "relaxed" : "strict" ) << " math, " << ( ( mathMode & 2 ) ? "generic" : "table" ) << " gradients\n"
                 << "#define FN2_RELAXED " << ( mathMode & 1 ) << "\n"
                 << "#define FN2_TABLES " << ( ( mathMode & 2 ) ? 0 : 1 ) << "\n"
                 << "#ifndef FN2_BLOCK\n#define FN2_BLOCK 256\n#endif\n"
-                << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP\n#endif\n"
+                << "#ifndef FN2_MIN_BLOCKS_ARG\n#define FN2_MIN_BLOCKS_ARG\n#endif\n"
+                << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP " << ( width == 2 ? "_Pragma( \"unroll\" )" : "" ) << "\n#endif\n"
+                << "#define FN2_W " << width << "\n"
                 << "#include \"fn2_device.cuh\"\n\n"
+                << "// value types of the node functions below: one point (float) or two points (packed FP32) per value\n"
+                << ( width == 2 ? "typedef fn2::fpair F;\ntypedef fn2::ipair I;\ntypedef fn2::bpair B;\n\n" : "typedef float F;\ntypedef fn2::i32 I;\ntypedef bool B;\n\n" )
                 << emitter.out.str();
 
             if( entryKind == kTileable2D ) src << TileEntry( rootFn, pointsPerThread );

@@ -92,6 +92,11 @@ FASTNOISE_API double fnb200MeasureAluPeak( int mode, int iters );
  * 1/sqrt sequence for EVERY float in [lo, hi). Returns the number of differing values (0 = identical), < 0 on a CUDA error. */
 FASTNOISE_API long long fnb200SelfTestInvSqrt( float lo, float hi );
 
+/* Self-test: evaluates leaf function `which` (0-23: simplex / supersimplex / perlin / value / white / cellular / gradient warp /
+ * misc, see csrc/device_check.cu) of the ahead-of-time compiled device library at n points (n even) into hostOut, either one
+ * point per value (packed = 0) or two points per value with packed FP32 instructions (packed = 1). The two must agree bit for bit. */
+FASTNOISE_API int fnb200SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut );
+
 /* Decodes `encodedString` into NodeData records (Metadata::DeserialiseNodeData) and serialises them again
  * (Metadata::SerialiseNodeData): the canonical spelling of a tree. Writes a NUL-terminated string into buf
  * (truncated to bufSize) and returns its full length, 0 if the input does not decode. */

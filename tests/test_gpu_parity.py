@@ -418,3 +418,75 @@ def test_concurrent_calls_from_threads(gpu):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_packed_leaves_equal_scalar_leaves(gpu):
+    """Every leaf of the device library evaluated two points per value (packed FP32: FFMA2 / FMUL2 / FADD2 for the arithmetic,
+    lane by lane for everything else) must give the bits of the one-point-per-value instantiation."""
+    n = 1 << 16
+    failures = []
+    for which in range(24):
+        for step in (0.37, 0.011):
+            a, b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+            assert gpu.lib.fnb200SelfTestLeaf(0, which, n, 1337, step, a.ctypes.data) == 0
+            assert gpu.lib.fnb200SelfTestLeaf(1, which, n, 1337, step, b.ctypes.data) == 0
+            if not np.array_equal(bits(a), bits(b)):
+                failures.append((which, step, helpers.compare(b, a)))
+    assert not failures, failures
+
+
+@pytest.fixture
+def force_packed():
+    """Small test grids normally run one point per thread; this makes them take the code path of large calls (4 points per
+    thread) with two points per value (packed FP32) in every dimension, which production only uses for 3D."""
+    saved = {k: os.environ.get(k) for k in ("FASTNOISE2_B200_PACK", "FASTNOISE2_B200_FILL")}
+    os.environ["FASTNOISE2_B200_PACK"] = "1"
+    os.environ["FASTNOISE2_B200_FILL"] = "0"
+    yield
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def test_packed_path_every_node_and_random_trees(gpu, ref, force_packed):
+    """The packed-FP32 instantiation of the whole node library: every node type in 2D/3D/4D with constant and generated
+    hybrids, plus 60 random trees, bit for bit against the oracle."""
+    from tests.fuzz import TreeFuzzer, same
+    failures = []
+    for node_id in range(47):
+        for dim, n in ((2, 64), (3, 20), (4, 9)):
+            a, b = trees.Tree(gpu.lib), trees.Tree(ref)
+            ha, hb = a.wire(node_id, node_id % 2 == 1), b.wire(node_id, node_id % 2 == 1)
+            outs = []
+            for lib, h in ((gpu.lib, ha), (ref, hb)):
+                out = np.empty(n ** dim, np.float32)
+                if dim == 2:
+                    lib.fnGenUniformGrid2D(h, out.ctypes.data, -3.3, 2.1, n, n, 1.9, 1.9, 1337, None)
+                elif dim == 3:
+                    lib.fnGenUniformGrid3D(h, out.ctypes.data, -3.3, 2.1, 0.7, n, n, n, 1.9, 1.9, 1.9, 1337, None)
+                else:
+                    lib.fnGenUniformGrid4D(h, out.ctypes.data, -3.3, 2.1, 0.7, -1.9, n, n, n, n, 1.9, 1.9, 1.9, 1.9, 1337, None)
+                outs.append(out)
+            if not same(outs[0], outs[1]):
+                failures.append((node_id, dim, helpers.compare(outs[0], outs[1])))
+            a.close()
+            b.close()
+    fuzzer = TreeFuzzer(777)
+    for index in range(40):
+        text = fuzzer.tree(depth=3).encode()
+        a, b = helpers.ProductNode(gpu, text), helpers.RefNode(ref, text)
+        for dim, got, want in ((2, a.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, index)[0], b.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, index)[0]),
+                               (3, a.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, index)[0], b.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, index)[0]),
+                               (4, a.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, index)[0])):
+            if not same(got, want):
+                failures.append((index, dim, text, helpers.compare(got, want)))
+        if index % 4 == 0:
+            rng = np.random.default_rng(index)
+            pos = [rng.uniform(-300, 300, 1537).astype(np.float32) for _ in range(3)]
+            if not same(a.positions(pos, [0.5, -1.5, 2.5], index)[0], b.positions(pos, [0.5, -1.5, 2.5], index)[0]):
+                failures.append((index, "positions3d", text))
+            if not same(a.tileable2d(40, 24, 1.3, 0.9, index)[0], b.tileable2d(40, 24, 1.3, 0.9, index)[0]):
+                failures.append((index, "tileable2d", text))
+    assert not failures, failures[:5]
