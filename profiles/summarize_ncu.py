@@ -37,6 +37,24 @@ def read_report(path):
     return out
 
 
+def packed_thread_instructions(path):
+    """Thread-instructions of the packed FP32 opcodes (FFMA2 / FMUL2 / FADD2): each does two lane-operations."""
+    text = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(text[text.index('"Address"'):])))
+    header = rows[0]
+    isrc, ithread = header.index("Source"), header.index("Thread Instructions Executed")
+    total = 0
+    for r in rows[1:]:
+        if len(r) <= ithread:
+            continue
+        src = r[isrc].strip()
+        if src.startswith("@"):
+            src = src.split(" ", 1)[1].strip()
+        if src.split()[0].split(".")[0] in ("FFMA2", "FMUL2", "FADD2"):
+            total += int(r[ithread])
+    return total
+
+
 def main():
     tag = sys.argv[1]
     here = os.path.dirname(os.path.abspath(__file__))
@@ -53,17 +71,19 @@ def main():
             points *= n
         m["points_per_launch"] = points
         m["thread_inst_per_point"] = m["smsp__inst_executed.sum"] * m["smsp__thread_inst_executed_per_inst_executed.ratio"] / points
+        m["packed_thread_inst_per_point"] = packed_thread_instructions(path) / points
+        m["lane_ops_per_point"] = m["thread_inst_per_point"] + m["packed_thread_inst_per_point"]  # a packed instruction = 2 lane-operations
     json.dump(summary, open(os.path.join(here, "%s_ncu_summary.json" % tag), "w"), indent=1)
     lines = ["# ncu --set full --clock-control none, kernel fn2_entry (one launch per workload), round %s" % tag, "",
-             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | lsu pipe % | tensor % | thread-inst/point | DRAM read | DRAM write | local ld/st |",
+             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | lsu pipe % | tensor % | thread-inst/point (of which packed) | DRAM read | DRAM write | local ld/st |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for w, m in summary.items():
-        lines.append("| %s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.3g B | %.3g B | %d/%d |" % (
+        lines.append("| %s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f (%.1f) | %.3g B | %.3g B | %d/%d |" % (
             w, m["gpu__time_duration.sum"] * 1e3, m["launch__registers_per_thread"], m["sm__warps_active.avg.pct_of_peak_sustained_active"],
             m["smsp__issue_active.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
             m["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"],
             m.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", 0),
-            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["thread_inst_per_point"], m.get("dram__bytes_read.sum", 0),
+            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["thread_inst_per_point"], m["packed_thread_inst_per_point"], m.get("dram__bytes_read.sum", 0),
             m.get("dram__bytes_write.sum", 0), m.get("sass__inst_executed_local_loads", 0), m.get("sass__inst_executed_local_stores", 0)))
     open(os.path.join(here, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
