@@ -5,7 +5,9 @@
 // is turned into straight-line device code: one `n<K>_<D>` function per (node, dimensionality) reached,
 // with every uniform parameter folded in as a literal and every uniform branch of the reference (distance
 // function, return type, interpolation, "is this hybrid a node?") resolved while generating. The functions
-// call the hand-written bodies in device/fn2_device*.cuh. Shared sub-trees are emitted once. The entry
+// are written against the value types F / I / B -- float / int / bool for one point per value, or the
+// fpair / ipair / bpair of device/fn2_device_pack.cuh for two points per value (packed FP32), chosen per
+// kernel by LowerTree -- and call the hand-written bodies in device/fn2_device*.cuh. Shared sub-trees are emitted once. The entry
 // kernel appended at the end is the batch driver for one call shape (grid 2/3/4D, tileable, positions).
 #include <FastNoise/FastNoise.h>
 #include <FastNoise/Metadata.h>
