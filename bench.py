@@ -373,7 +373,7 @@ def main():
     ref_ops = w["ops"] * points / (kernel_ms * 1e-3) / 1e12
     # lane-operations = thread-instructions, with a packed FP32 instruction (FFMA2 / FMUL2 / FADD2) counted as the two it performs --
     # the unit the peak is measured in (FFMA lane-ops/s; FFMA2 reaches the same lane-op rate with half the instructions)
-    achieved = ((inst_per_point + packed_per_point) if inst_per_point else w["ops"]) * points / (kernel_ms * 1e-3) / 1e12
+    achieved = (inst_per_point + packed_per_point) * points / (kernel_ms * 1e-3) / 1e12 if inst_per_point else None
     issue_frac = inst_per_point * points / (kernel_ms * 1e-3) / alu_peak if inst_per_point and alu_peak else None
     peak = alu_peak / 1e12
     store_gbs = out_bytes / (kernel_ms * 1e-3) / 1e9
@@ -386,9 +386,9 @@ def main():
                    "points_per_gpu": points, "sharding": "z-slab (outermost axis) per rank, global integer indices" if world > 1 else "none",
                    "math": args.math, "l2": "output per step (%d MiB) exceeds L2; no inputs are re-read" % (out_bytes >> 20),
                    "output_minmax": [lo, hi]},
-        "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak if peak else None, "issue_slot_frac": issue_frac,
+        "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak if peak and achieved else None, "issue_slot_frac": issue_frac,
                      "achieved_is": ("lane-operations per second = (%.1f thread-inst/point, of which %.1f packed FP32 counted twice; profiles/r1_ncu_summary.json, ncu) x points / kernel time" % (inst_per_point, packed_per_point)) if inst_per_point
-                     else "reference lane-ops per second (SURVEY 8d ops/point x points / kernel time); no ncu instruction count committed for this workload+mode",
+                     else "no ncu instruction count is committed for this workload + math mode (profiles/r1_ncu_summary.json): see reference_ops",
                      "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)" if traffic else None,
                      "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-specialised tree kernel)", "kernel_ms": kernel_ms,
                      "inst_per_point": inst_per_point,

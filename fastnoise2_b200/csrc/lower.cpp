@@ -853,12 +853,14 @@ namespace FastNoise
             }
 
             // Two points per value (packed FP32) or one? Packing removes ~20 % of the issued instructions, but a value then takes
-            // a register pair and the kernels end up at 100-250 registers. Measured on B200: a gain for trees
-            // evaluated in 3D (C1 +3 %, C3a +4 %, C4 +3 %), a wash in 2D, a loss in 4D where the lattice functions already
-            // need ~100 registers one point at a time. FASTNOISE2_B200_PACK=0/1 forces it off/on.
+            // a register pair, the kernels end up at 100-250 registers and, with the octave loops unrolled, ~90 KB of code.
+            // Measured on B200: for trees evaluated in 3D +3 % on some boxes and -5 % on others with the
+            // SAME cubin (the scalar kernel is stable), a wash in 2D, a loss in 4D; the JIT takes up to 6x longer. It is
+            // therefore opt-in: FASTNOISE2_B200_PACK=1 enables it for 3D calls, =2 for every dimension.
             const int entryDim = entryKind == kTileable2D ? 4 : ( entryKind >= 10 ? entryKind - 10 : entryKind );
             const char* packEnv = std::getenv( "FASTNOISE2_B200_PACK" );
-            const bool pack = packEnv && *packEnv ? std::atoi( packEnv ) != 0 : entryDim == 3;
+            const int packMode = packEnv && *packEnv ? std::atoi( packEnv ) : 0;
+            const bool pack = packMode >= 2 || ( packMode == 1 && entryDim == 3 );
             const int width = pointsPerThread >= 2 && pack ? 2 : 1;
 
             std::ostringstream src;

@@ -438,9 +438,9 @@ def test_packed_leaves_equal_scalar_leaves(gpu):
 @pytest.fixture
 def force_packed():
     """Small test grids normally run one point per thread; this makes them take the code path of large calls (4 points per
-    thread) with two points per value (packed FP32) in every dimension, which production only uses for 3D."""
+    thread) with two points per value (packed FP32) in every dimension (opt-in in production: FASTNOISE2_B200_PACK)."""
     saved = {k: os.environ.get(k) for k in ("FASTNOISE2_B200_PACK", "FASTNOISE2_B200_FILL")}
-    os.environ["FASTNOISE2_B200_PACK"] = "1"
+    os.environ["FASTNOISE2_B200_PACK"] = "2"
     os.environ["FASTNOISE2_B200_FILL"] = "0"
     yield
     for k, v in saved.items():
