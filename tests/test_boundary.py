@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -120,6 +121,38 @@ def test_every_config_tree_lowers_and_compiles_for_sm100a(fn):
             src = g.kernel_source(kind)
             assert "fn2_entry" in src and "#include \"fn2_device.cuh\"" in src
             g.prepare(kind)
+
+
+def test_packed_form_compiles_without_fused_packed_products(fn, tmp_path):
+    """The opt-in two-points-per-value form (FASTNOISE2_B200_PACK) must compile for every dimensionality, must actually use
+    the packed FP32 instructions, and -- in strict mode -- must not contain a single FMUL2: ptxas contracts a packed multiply
+    with a following packed add into one FFMA2 whatever --fmad says, so packed products are issued as FFMA2( a, b, -0 ) and an
+    FMUL2 in the SASS would mean a product that can be fused, i.e. a rounding the reference does not have."""
+    import glob
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    code = r'''
+import os, sys
+os.environ["FASTNOISE2_B200_CACHE"] = sys.argv[1]
+os.environ["FASTNOISE2_B200_PACK"] = "2"
+sys.path.insert(0, %r)
+import fastnoise2_b200 as fn
+from fastnoise2_b200 import api
+for name, kind in (("c4_terrain", api.KIND_GRID3D), ("c2_fbm5_perlin", api.KIND_GRID2D), ("c3a_cellular_distance", api.KIND_GRID3D), ("c5_supersimplex", api.KIND_GRID4D)):
+    g = fn.Generator(fn.TREES[name])
+    assert "typedef fn2::fpair F;" in g.kernel_source(kind)
+    g.prepare(kind)
+print("ok")
+''' % ROOT
+    result = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True)
+    assert result.returncode == 0 and result.stdout.strip().endswith("ok"), result.stderr[-2000:]
+    cubins = glob.glob(str(tmp_path / "*.cubin"))
+    assert len(cubins) == 4
+    for cubin in cubins:
+        sass = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout
+        assert "FFMA2" in sass and "FADD2" in sass
+        assert "FMUL2" not in sass
 
 
 def test_incomplete_tree_fails_loudly(fn):
