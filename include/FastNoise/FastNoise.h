@@ -3,17 +3,18 @@
 #pragma once
 #include "Utility/Config.h"
 
-#include "Generators/BasicGenerators.h"
-#include "Generators/Value.h"
+// node classes, by family
+#include "Generators/BasicGenerators.h"   // Constant White Checkerboard SineWave Gradient DistanceToPoint
+#include "Generators/Blends.h"            // Add ... Fade, PowFloat / PowInt, Min/MaxSmooth
+#include "Generators/Cellular.h"          // CellularValue / Distance / Lookup
+#include "Generators/DomainWarp.h"        // DomainWarpGradient
+#include "Generators/DomainWarpFractal.h" // DomainWarpFractalProgressive / Independent
+#include "Generators/DomainWarpSimplex.h" // DomainWarpSimplex / SuperSimplex
+#include "Generators/Fractal.h"           // FractalFBm / Ridged
+#include "Generators/Modifiers.h"         // Domain*, Remap, Terrace, SeedOffset, ...
 #include "Generators/Perlin.h"
-#include "Generators/Simplex.h"
-#include "Generators/Cellular.h"
-#include "Generators/Fractal.h"
-#include "Generators/DomainWarp.h"
-#include "Generators/DomainWarpSimplex.h"
-#include "Generators/DomainWarpFractal.h"
-#include "Generators/Modifiers.h"
-#include "Generators/Blends.h"
+#include "Generators/Simplex.h"           // Simplex / SuperSimplex
+#include "Generators/Value.h"
 
 namespace FastNoise
 {
