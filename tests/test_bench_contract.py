@@ -1,0 +1,36 @@
+"""bench.py contract, as far as it can be checked without a GPU: the reference arm (the reference's node code on the host
+cores) runs, prints exactly one JSON line and carries the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    if helpers.load_ref("relaxed_avx2") is None and helpers.load_ref("relaxed_avx512") is None:
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "Mpoints/s" and line["higher_is_better"] is True and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 times the CPU reference; the other ranks print nothing and exit 0."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == "", (out.stdout, out.stderr[-500:])
