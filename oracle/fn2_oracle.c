@@ -364,7 +364,8 @@ static i32 asr( i32 a, int s ) { return a >> s; } /* arithmetic on every compile
 static i32 f2b( float v ) { i32 b; memcpy( &b, &v, 4 ); return b; }
 static float b2f( i32 b ) { float v; memcpy( &v, &b, 4 ); return v; }
 static float fxor( float v, i32 bits ) { return b2f( f2b( v ) ^ bits ); }
-static i32 cvt_i( float v ) { return (i32)lrintf( v ); }  /* FS::Convert<int32_t>: cvtps2dq, nearest even */
+/* FS::Convert<int32_t> = cvtps2dq: round to nearest even; NaN and anything outside [-2^31, 2^31) give the "integer indefinite" 0x80000000 */
+static i32 cvt_i( float v ) { return ( v >= -2147483648.0f && v < 2147483648.0f ) ? (i32)lrintf( v ) : (i32)0x80000000u; }
 static float fmin_x86( float a, float b ) { return a < b ? a : b; } /* minps operand order */
 static float fmax_x86( float a, float b ) { return a > b ? a : b; }
 static float fnma( float a, float b, float c ) { return fmaf( -a, b, c ); }

@@ -43,6 +43,8 @@ class TreeFuzzer:
                 node_id = int(self.rng.choice(LEAF_IDS[1:] if self.rng.random() < 0.9 else LEAF_IDS))  # Constant only now and then
             else:
                 node_id = int(self.rng.integers(0, 47))
+                while node_id == 38:                # ConvertRGBA8 packs bytes into float BIT PATTERNS (NaNs, infinities, 1e38): below the
+                    node_id = int(self.rng.integers(0, 47))  # root it would feed those to positions, where the reference itself is lane-order garbage
         meta = _META[node_id]
         variables = {}
         for v in meta["variables"]:
