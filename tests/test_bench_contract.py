@@ -34,3 +34,15 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == "", (out.stdout, out.stderr[-500:])
+
+
+def test_node_benchmark_reference_arm_runs():
+    """tools/node_benchmark.py (the FastNoiseBenchmark-shaped harness) on the CPU reference arm, two nodes, reference naming."""
+    if helpers.load_ref("relaxed_avx2") is None and helpers.load_ref("relaxed_avx512") is None:
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "node_benchmark.py"), "--impl", "reference", "--filter", "Perlin", "--dims", "2", "3",
+                          "--positions", "1024", "--iterations", "3", "--cpu-seconds", "0.05"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.strip()]
+    assert len(lines) == 2 and lines[0].startswith("2D/") and lines[1].startswith("3D/")
+    assert all("/Coherent Noise/Perlin" in line and "M items/s" in line for line in lines)
