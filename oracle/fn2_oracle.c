@@ -9,9 +9,11 @@
  *
  * Arithmetic contract = the STRICT semantics of oracle/shim (the stand-in for the absent FastSIMD dependency,
  * Auburn/FastSIMD @ 16450dae9528727e500e7254f635a671f9c7ee2d): IEEE single ops, fmaf exactly where the reference has
- * FS::FMulAdd/FNMulAdd/FMulSub, Convert<int> = round-to-nearest-even, InvSqrt = 1/sqrt, generic (non-table)
- * gradient code paths. Pinned by tests/test_oracle.py against tests/golden/ (vectors produced by the reference's
- * own sources compiled over that shim). The reference's tests hold no expected values: PARITY UNPINNED upstream.
+ * FS::FMulAdd/FNMulAdd/FMulSub, Convert<int> = cvtps2dq (round-to-nearest-even, 0x80000000 when out of range),
+ * InvSqrt = 1/sqrt, and BOTH gradient flavours of the reference (fn2oSetFlavor: 0 = generic select/xor code paths,
+ * 1 = the AVX512_F permute-table code paths). Pinned by tests/test_oracle.py against tests/golden/ (vectors produced
+ * by the reference's own sources compiled over that shim, one set per flavour) and against those sources directly on
+ * every node type and on fuzzed trees. The reference's tests hold no expected values: PARITY UNPINNED upstream.
  *
  * Build: gcc -O2 -std=c99 -ffp-contract=off -mfma -fPIC -shared fn2_oracle.c -o libfn2oracle.so -lm
  */
