@@ -269,3 +269,40 @@ def test_public_headers_parse_as_cpp11(tmp_path):
     src = tmp_path / "inc.cpp"
     src.write_text("#include <FastNoise/FastNoise.h>\n#include <FastNoise/Metadata.h>\n#include <FastNoise/FastNoise_C.h>\nint main() { return 0; }\n")
     subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)])
+
+
+def test_canonical_reencoding_preserves_random_trees(fn, ref):
+    """Codec fuzz: 300 random trees (all node types, generator hybrids, shared sub-trees -> back-references) are decoded and
+    re-encoded by the product; the reference's own decoder must build a tree from the re-encoded string that evaluates to
+    exactly the same values as the original string."""
+    from tests.encode import N
+    from tests.fuzz import TreeFuzzer, same
+
+    def hits_metadata_default_quirk(node, seen):
+        # DistanceToPoint is constructed with EuclideanSquared but its metadata default says Euclidean
+        # (BasicGenerators.h:289 vs :305), and the serialiser omits values equal to the METADATA default: an explicit
+        # Euclidean does not survive a round trip in the reference either. Reproduced, so such trees are skipped here.
+        if id(node) in seen:
+            return False
+        seen.add(id(node))
+        if node.meta["name"] == "DistanceToPoint" and node.variables.get("Distance Function") == 0:
+            return True
+        children = list(node.lookups) + [h for h in node.hybrids.values() if isinstance(h, N)]
+        return any(hits_metadata_default_quirk(c, seen) for c in children)
+
+    fuzzer = TreeFuzzer(31337)
+    buf = ctypes.create_string_buffer(1 << 16)
+    checked = 0
+    for index in range(300):
+        tree = fuzzer.tree(depth=3 if index % 4 else 4)
+        if hits_metadata_default_quirk(tree, set()):
+            continue
+        checked += 1
+        text = tree.encode()
+        n = fn.lib.fnb200CanonicalEncodedNodeTree(text.encode(), buf, len(buf))
+        assert n > 0, text
+        canon = buf.value.decode()
+        a, b = helpers.RefNode(ref, text), helpers.RefNode(ref, canon)
+        assert same(a.grid3d(-3.3, 2.1, 0.7, 6, 6, 6, 1.9, 1.7, 2.3, index)[0], b.grid3d(-3.3, 2.1, 0.7, 6, 6, 6, 1.9, 1.7, 2.3, index)[0]), (text, canon)
+        assert same(a.grid2d(-3.3, 2.1, 12, 12, 1.9, 1.7, index)[0], b.grid2d(-3.3, 2.1, 12, 12, 1.9, 1.7, index)[0]), (text, canon)
+    assert checked > 250
