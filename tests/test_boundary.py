@@ -306,3 +306,30 @@ def test_canonical_reencoding_preserves_random_trees(fn, ref):
         assert same(a.grid3d(-3.3, 2.1, 0.7, 6, 6, 6, 1.9, 1.7, 2.3, index)[0], b.grid3d(-3.3, 2.1, 0.7, 6, 6, 6, 1.9, 1.7, 2.3, index)[0]), (text, canon)
         assert same(a.grid2d(-3.3, 2.1, 12, 12, 1.9, 1.7, index)[0], b.grid2d(-3.3, 2.1, 12, 12, 1.9, 1.7, index)[0]), (text, canon)
     assert checked > 250
+
+
+def test_decoder_agrees_with_reference_on_mutated_trees(fn, ref):
+    """Decoder robustness: valid random trees with one to three bytes corrupted (or truncated) reach deep into both decoders;
+    accept / reject decisions and the decoded root type must match the reference's, and neither may crash."""
+    import base64
+    from tests.fuzz import TreeFuzzer
+    fuzzer = TreeFuzzer(99)
+    rng = np.random.default_rng(99)
+    accepted = rejected = 0
+    for index in range(400):
+        raw = bytearray(base64.b64decode(fuzzer.tree(depth=3).encode()))
+        for _ in range(int(rng.integers(1, 4))):
+            raw[int(rng.integers(len(raw)))] = int(rng.integers(256))
+        if index % 5 == 0:
+            raw = raw[:int(rng.integers(1, len(raw) + 1))]
+        text = base64.b64encode(bytes(raw))
+        ours = fn.lib.fnNewFromEncodedNodeTree(text, 0xFFFFFFFF)
+        theirs = ref.fnNewFromEncodedNodeTree(text, 0xFFFFFFFF)
+        assert (ours is None) == (theirs is None), (bytes(raw).hex(), ours, theirs)
+        if ours:
+            assert fn.lib.fnGetMetadataID(ours) == ref.fnGetMetadataID(theirs)
+            fn.lib.fnDeleteNodeRef(ours)
+            accepted += 1
+        else:
+            rejected += 1
+    assert accepted > 20 and rejected > 20, (accepted, rejected)
