@@ -333,3 +333,51 @@ def test_decoder_agrees_with_reference_on_mutated_trees(fn, ref):
         else:
             rejected += 1
     assert accepted > 20 and rejected > 20, (accepted, rejected)
+
+
+def test_reflection_setters_build_the_same_program_as_the_decoder(fn):
+    """150 random trees built twice -- through fnNewFromMetadata + fnSetVariable* / fnSetNodeLookup / fnSetHybrid* (what the
+    Node Editor and every binding do) and by decoding the encoded string -- must lower to the same CUDA source, in 2D, 3D
+    and 4D: member indices, setter side effects (scale -> frequency, output range, rotations ...) and shared sub-trees agree."""
+    from tests.encode import N
+    from tests.fuzz import TreeFuzzer
+    lib = fn.lib
+    created = []
+
+    def build(node, done):
+        if id(node) in done:
+            return done[id(node)]
+        meta = node.meta
+        h = lib.fnNewFromMetadata(meta["id"], 0xFFFFFFFF)
+        assert h
+        created.append(h)
+        for key, value in node.variables.items():
+            i = N._index(meta["variables"], key)
+            if meta["variables"][i]["type"] == 0:
+                assert lib.fnSetVariableFloat(h, i, value)
+            else:
+                assert lib.fnSetVariableIntEnum(h, i, value)
+        for i, child in enumerate(node.lookups):
+            assert lib.fnSetNodeLookup(h, i, build(child, done)), (meta["name"], i)
+        for key, value in node.hybrids.items():
+            i = N._index(meta["hybrids"], key)
+            if isinstance(value, N):
+                assert lib.fnSetHybridNodeLookup(h, i, build(value, done))
+            else:
+                assert lib.fnSetHybridFloat(h, i, value)
+        done[id(node)] = h
+        return h
+
+    fuzzer = TreeFuzzer(2718)
+    for index in range(150):
+        tree = fuzzer.tree(depth=3)
+        decoded = fn.Generator(tree.encode())
+        root = build(tree, {})
+        for kind in (2, 3, 4):
+            n = lib.fnb200GetKernelSource(root, kind, None, 0)
+            assert n > 0, fn.last_error()
+            buf = ctypes.create_string_buffer(n + 1)
+            lib.fnb200GetKernelSource(root, kind, buf, n + 1)
+            assert buf.value.decode() == decoded.kernel_source(kind), (index, kind, tree.encode())
+    for h in created:
+        lib.fnDeleteNodeRef(h)
