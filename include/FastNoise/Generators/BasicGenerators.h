@@ -101,6 +101,9 @@ namespace FastNoise
     class DistanceToPoint : public NodeBase
     {
         FN2_NODE( DistanceToPoint, 5 )
+        /// Accepted for source compatibility and ignored: the reference declares it (BasicGenerators.h:266) but never
+        /// evaluates, reflects or serialises that source.
+        void SetSource( SmartNodeArg<> ) {}
         void SetDistanceFunction( DistanceFunction value ) { SetVar( 0, (int)value ); }
         void SetMinkowskiP( SmartNodeArg<> gen ) { SetHyb( 4, gen.get() ); }
         void SetMinkowskiP( float value ) { SetHyb( 4, value ); }
