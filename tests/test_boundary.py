@@ -398,3 +398,24 @@ def test_every_reference_setter_compiles_against_these_headers(tmp_path):
     if os.path.isdir("/root/reference/include"):
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-w", "-mavx2", "-mfma", "-I" + os.path.join(ROOT, "oracle", "shim"),
                                "-I/root/reference/include", source])
+
+
+def test_c_abi_prototypes_are_compatible_with_the_reference_header(tmp_path):
+    """Both FastNoise_C.h headers in ONE translation unit: a prototype here that differed from the reference's in any argument or
+    return type would be a "conflicting types" error (C) / an ambiguous overload with C linkage (C++)."""
+    reference = "/root/reference/include/FastNoise/FastNoise_C.h"
+    if not os.path.exists(reference):
+        pytest.skip("reference headers not present")
+    ours = os.path.join(ROOT, "include", "FastNoise", "FastNoise_C.h")
+    c = tmp_path / "both.c"
+    c.write_text('#include <stdbool.h>\n#include "%s"\n#include "%s"\nint main(void) { return 0; }\n' % (reference, ours))
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(c)])  # macro redefinitions of the two Export.h are fine
+    cpp = tmp_path / "both.cpp"
+    cpp.write_text('#include "%s"\n#include "%s"\nint main() { return 0; }\n' % (reference, ours))
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(cpp)])
+    # every function the reference declares is declared (and exported) here
+    names = set(re.findall(r"FASTNOISE_API\s+[\w\s\*]+?\b(fn\w+)\s*\(", open(reference).read()))
+    assert len(names) == 45
+    exported = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "fastnoise2_b200", "libfastnoise2_b200.so")], capture_output=True, text=True).stdout
+    missing = [n for n in sorted(names) if (" T " + n + "\n") not in exported]
+    assert not missing, missing
