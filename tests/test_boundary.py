@@ -419,3 +419,72 @@ def test_c_abi_prototypes_are_compatible_with_the_reference_header(tmp_path):
     exported = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "fastnoise2_b200", "libfastnoise2_b200.so")], capture_output=True, text=True).stdout
     missing = [n for n in sorted(names) if (" T " + n + "\n") not in exported]
     assert not missing, missing
+
+
+def test_reflection_getters_match_live_reference_including_invalid_arguments(fn, ref):
+    """Every reflection getter of the C ABI, for every node id from -2 to 48 and every member index from -2 to count+1, returns
+    what the reference returns -- valid values, and the "INVALID ..." strings / -1 / 0 conventions for bad ids and indices.
+    (Descriptions are this repo's own wording for valid members, so only their INVALID forms are compared.)"""
+    a, b = fn.lib, ref
+    ids = range(-2, 49)
+
+    def both(name, *args):
+        x, y = getattr(a, name)(*args), getattr(b, name)(*args)
+        if isinstance(x, float) or isinstance(y, float):
+            assert (x == y) or (x != x and y != y), (name, args, x, y)
+        else:
+            assert x == y, (name, args, x, y)
+        return x
+
+    assert both("fnGetMetadataCount") == 47
+    for node in ids:
+        both("fnGetMetadataName", node)
+        groups = both("fnGetMetadataGroupCount", node)
+        for g in range(-2, max(groups, 0) + 2):
+            both("fnGetMetadataGroupName", node, g)
+        variables = both("fnGetMetadataVariableCount", node)
+        for v in range(-2, max(variables, 0) + 2):
+            both("fnGetMetadataVariableName", node, v)
+            both("fnGetMetadataVariableType", node, v)
+            both("fnGetMetadataVariableDimensionIdx", node, v)
+            both("fnGetMetadataVariableDefaultFloat", node, v)
+            both("fnGetMetadataVariableDefaultIntEnum", node, v)
+            both("fnGetMetadataVariableMinFloat", node, v)
+            both("fnGetMetadataVariableMaxFloat", node, v)
+            enums = both("fnGetMetadataEnumCount", node, v)
+            for e in range(-2, max(enums, 0) + 2):
+                both("fnGetMetadataEnumName", node, v, e)
+        lookups = both("fnGetMetadataNodeLookupCount", node)
+        for i in range(-2, max(lookups, 0) + 2):
+            both("fnGetMetadataNodeLookupName", node, i)
+            both("fnGetMetadataNodeLookupDimensionIdx", node, i)
+        hybrids = both("fnGetMetadataHybridCount", node)
+        for i in range(-2, max(hybrids, 0) + 2):
+            both("fnGetMetadataHybridName", node, i)
+            both("fnGetMetadataHybridDimensionIdx", node, i)
+            both("fnGetMetadataHybridDefault", node, i)
+    for node in (-2, -1, 47, 48):                   # descriptions: only the invalid-argument conventions are the reference's
+        both("fnGetMetadataDescription", node)
+        both("fnGetMetadataVariableDescription", node, 0)
+        both("fnGetMetadataNodeLookupDescription", node, 0)
+        both("fnGetMetadataHybridDescription", node, 0)
+    for node in (6, 13):
+        for bad in (-1, 99):
+            both("fnGetMetadataVariableDescription", node, bad)
+            both("fnGetMetadataNodeLookupDescription", node, bad)
+            both("fnGetMetadataHybridDescription", node, bad)
+    # setters and factories with invalid arguments
+    for lib in (a, b):
+        assert lib.fnNewFromMetadata(-1, 0xFFFFFFFF) is None and lib.fnNewFromMetadata(47, 0xFFFFFFFF) is None
+        assert lib.fnNewFromEncodedNodeTree(b"", 0xFFFFFFFF) is None
+    ha, hb = a.fnNewFromMetadata(13, 0xFFFFFFFF), b.fnNewFromMetadata(13, 0xFFFFFFFF)
+    ca, cb = a.fnNewFromMetadata(0, 0xFFFFFFFF), b.fnNewFromMetadata(0, 0xFFFFFFFF)
+    for index in (-1, 0, 1, 2, 7):
+        assert bool(a.fnSetVariableFloat(ha, index, 2.0)) == bool(b.fnSetVariableFloat(hb, index, 2.0)), index
+        assert bool(a.fnSetVariableIntEnum(ha, index, 3)) == bool(b.fnSetVariableIntEnum(hb, index, 3)), index
+        assert bool(a.fnSetNodeLookup(ha, index, ca)) == bool(b.fnSetNodeLookup(hb, index, cb)), index
+        assert bool(a.fnSetHybridFloat(ha, index, 0.5)) == bool(b.fnSetHybridFloat(hb, index, 0.5)), index
+        assert bool(a.fnSetHybridNodeLookup(ha, index, ca)) == bool(b.fnSetHybridNodeLookup(hb, index, cb)), index
+    assert a.fnGetMetadataID(ha) == b.fnGetMetadataID(hb) == 13
+    for lib, h in ((a, ha), (a, ca), (b, hb), (b, cb)):
+        lib.fnDeleteNodeRef(h)
