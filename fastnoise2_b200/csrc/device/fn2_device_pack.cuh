@@ -100,9 +100,7 @@ namespace fn2
     {
         constexpr i32 mask = ( ( 1 << BITS ) - 1 ) << SHIFT;
         constexpr i32 magic = ( 127 + 23 - SHIFT ) << 23;
-        i32 mx, my;
-        asm( "lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"( mx ) : "r"( v.x ), "n"( mask ), "r"( magic ) );
-        asm( "lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"( my ) : "r"( v.y ), "n"( mask ), "r"( magic ) );
+        const i32 mx = FN2_LOP3_AND_OR( v.x, mask, magic ), my = FN2_LOP3_AND_OR( v.y, mask, magic );
         return fpair( __int_as_float( mx ), __int_as_float( my ) ) - fpair( __int_as_float( magic ) ); // the subtraction is packed
     }
     template<int SHIFT, int BITS>
@@ -110,26 +108,20 @@ namespace fn2
     {
         constexpr i32 mask = ( ( 1 << BITS ) - 1 ) << SHIFT;
         constexpr i32 magic = ( 127 + 23 - SHIFT ) << 23;
-        i32 mx, my;
-        asm( "lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"( mx ) : "r"( v.x ), "n"( mask ), "r"( magic ) );
-        asm( "lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"( my ) : "r"( v.y ), "n"( mask ), "r"( magic ) );
+        const i32 mx = FN2_LOP3_AND_OR( v.x, mask, magic ), my = FN2_LOP3_AND_OR( v.y, mask, magic );
         return fpair( __int_as_float( mx ), __int_as_float( my ) ) - fpair( __int_as_float( magic ) + centre );
     }
 
     FN2_DI fpair inv_sqrt_bounded( fpair v ) // see the scalar form: MUFU per lane, the Newton steps packed
     {
-#if FN2_RELAXED
-        return fpair( rsqrtf( v.x ), rsqrtf( v.y ) );
+#if FN2_RELAXED || defined( FN2_HOST_EMULATION )
+        return fpair( inv_sqrt_bounded( v.x ), inv_sqrt_bounded( v.y ) );
 #else
-        fpair y;
-        asm( "rsqrt.approx.ftz.f32 %0, %1;" : "=f"( y.x ) : "f"( v.x ) );
-        asm( "rsqrt.approx.ftz.f32 %0, %1;" : "=f"( y.y ) : "f"( v.y ) );
+        const fpair y( rsqrt_approx( v.x ), rsqrt_approx( v.y ) );
         fpair g = v * y;
         const fpair h = fpair( 0.5f ) * y;
         g = fma_( fnma_( g, g, v ), h, g );
-        fpair r;
-        asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r.x ) : "f"( g.x ) );
-        asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r.y ) : "f"( g.y ) );
+        const fpair r( rcp_approx( g.x ), rcp_approx( g.y ) );
         return fma_( r, fnma_( g, r, fpair( 1.0f ) ), r );
 #endif
     }
