@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- appended after a generated tree source: runs the entry kernel "thread" by "thread" on the host.
-// Grid entries only (kinds 2, 3, 4); the arguments are filled the way csrc/backend.cpp LaunchGridRows does.
+// FN2_HOST_ENTRY selects the driver for the entry kind of that source (0 uniform grid, 1 tileable, 2 position array); the
+// arguments are filled the way csrc/backend.cpp LaunchGridRows / LaunchPositions fill them.
 static fn2::FastDiv fn2_host_fast_div( unsigned d )
 {
     fn2::FastDiv fd { 0, 0, d, 0 };
@@ -11,23 +12,9 @@ static fn2::FastDiv fn2_host_fast_div( unsigned d )
     return fd;
 }
 
-extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int* count, const float* step, int seed, int pointsPerThread )
+template<class ARGS>
+static void fn2_host_launch( float* out, const ARGS& a, unsigned long long points, int pointsPerThread, int seed )
 {
-    fn2::GridArgs a {};
-    unsigned long long points = 1;
-    for( int d = 0; d < 4; d++ )
-    {
-        a.off[d] = d < dims ? off[d] : 0.0f;
-        a.step[d] = d < dims ? step[d] : 0.0f;
-        a.count[d] = d < dims ? count[d] : 1;
-        points *= (unsigned)a.count[d];
-    }
-    a.rowBegin = 0;
-    a.total = (unsigned)points;
-    a.vecStore = 0;
-    a.divX = fn2_host_fast_div( (unsigned)a.count[0] );
-    a.divY = fn2_host_fast_div( (unsigned)a.count[1] );
-    a.divZ = fn2_host_fast_div( (unsigned)a.count[2] );
     const unsigned long long threads = ( points + pointsPerThread - 1 ) / pointsPerThread;
     blockDim = { FN2_BLOCK, 1, 1 };
     gridDim = { (unsigned)( ( threads + FN2_BLOCK - 1 ) / FN2_BLOCK ), 1, 1 };
@@ -41,3 +28,54 @@ extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int
         }
     }
 }
+
+#if FN2_HOST_ENTRY == 0
+extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int* count, const float* step, int seed, int pointsPerThread )
+{
+    fn2::GridArgs a {};
+    unsigned long long points = 1;
+    for( int d = 0; d < 4; d++ )
+    {
+        a.off[d] = d < dims ? off[d] : 0.0f;
+        a.step[d] = d < dims ? step[d] : 0.0f;
+        a.count[d] = d < dims ? count[d] : 1;
+        points *= (unsigned)a.count[d];
+    }
+    a.total = (unsigned)points;
+    a.divX = fn2_host_fast_div( (unsigned)a.count[0] );
+    a.divY = fn2_host_fast_div( (unsigned)a.count[1] );
+    a.divZ = fn2_host_fast_div( (unsigned)a.count[2] );
+    fn2_host_launch( out, a, points, pointsPerThread, seed );
+}
+#elif FN2_HOST_ENTRY == 1
+extern "C" void fn2_host_tileable( float* out, int xSize, int ySize, float xStep, float yStep, int seed, int pointsPerThread )
+{
+    fn2::TileArgs a {};
+    const float pi2Recip = 0.15915493667f; // [Generator.inl:386-392], same float arithmetic as backend.cpp
+    const float xSizePi = (float)xSize * pi2Recip, ySizePi = (float)ySize * pi2Recip;
+    a.xFreq = xSizePi * xStep;
+    a.yFreq = ySizePi * yStep;
+    a.xMul = 1 / xSizePi;
+    a.yMul = 1 / ySizePi;
+    a.xSize = xSize;
+    a.ySize = ySize;
+    a.total = (unsigned)( xSize * ySize );
+    a.divX = fn2_host_fast_div( (unsigned)xSize );
+    fn2_host_launch( out, a, (unsigned long long)xSize * ySize, pointsPerThread, seed );
+}
+#else
+extern "C" void fn2_host_positions( float* out, int dims, long long count, const float* x, const float* y, const float* z, const float* w,
+                                    const float* off, int seed, int pointsPerThread )
+{
+    fn2::PosArgs a {};
+    const float* pos[4] = { x, y, z, w };
+    for( int d = 0; d < 4; d++ )
+    {
+        a.pos[d] = d < dims ? pos[d] : nullptr;
+        a.off[d] = d < dims ? off[d] : 0.0f;
+    }
+    a.count = (unsigned long long)count;
+    a.vecIO = 0;
+    fn2_host_launch( out, a, (unsigned long long)count, pointsPerThread, seed );
+}
+#endif

@@ -29,25 +29,48 @@ GRIDS = {2: dict(off=(-3.3, 2.1), n=(20, 13), step=(1.9, 1.7)),
 
 
 _BUILDS = [0]
+KIND_TILEABLE, KIND_POS = 5, 10
 
 
-def run_on_host(fn, text, dims, seed, workdir, tag):
-    """Lower `text` for a dims-D grid, compile the generated CUDA with g++ over the stand-in, run it, return the values."""
+def build_on_host(fn, text, kind, workdir, tag):
+    """Lower `text` for one entry kind, compile the generated CUDA with g++ over the stand-in; returns (library, points per thread)."""
     _BUILDS[0] += 1
     tag = "%s_%d" % (tag, _BUILDS[0])  # dlopen() hands back an already loaded library for a path it has seen
-    source = fn.Generator(text).kernel_source(dims)
+    source = fn.Generator(text).kernel_source(kind)
     ppt = int(source.split(" point(s) per thread")[0].rsplit(" ", 1)[1])
+    entry = 1 if kind == KIND_TILEABLE else (2 if kind > KIND_POS else 0)
     path = os.path.join(workdir, "tree_%s.cpp" % tag)
     with open(path, "w") as f:
-        f.write('#include "cuda_host_shim.h"\n' + source + '\n#include "driver.inl"\n')
+        f.write('#include "cuda_host_shim.h"\n' + source + '\n#define FN2_HOST_ENTRY %d\n#include "driver.inl"\n' % entry)
     lib_path = os.path.join(workdir, "tree_%s.so" % tag)
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fwrapv", "-w", "-fPIC", "-shared",
                            "-I" + os.path.join(ROOT, "tests", "host_emulation"), "-I" + os.path.join(ROOT, "fastnoise2_b200", "csrc", "device"), path, "-o", lib_path])
-    lib = ctypes.CDLL(lib_path)
+    return ctypes.CDLL(lib_path), ppt
+
+
+def run_on_host(fn, text, dims, seed, workdir, tag):
+    """dims-D uniform grid of GRIDS[dims] through the generated entry kernel, on the host."""
+    lib, ppt = build_on_host(fn, text, dims, workdir, tag)
     g = GRIDS[dims]
     out = np.zeros(int(np.prod(g["n"])), np.float32)
     lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), dims, (ctypes.c_float * dims)(*g["off"]), (ctypes.c_int * dims)(*g["n"]),
                       (ctypes.c_float * dims)(*g["step"]), seed, ppt)
+    return out
+
+
+def run_tileable_on_host(fn, text, nx, ny, sx, sy, seed, workdir, tag):
+    lib, ppt = build_on_host(fn, text, KIND_TILEABLE, workdir, tag)
+    out = np.zeros(nx * ny, np.float32)
+    lib.fn2_host_tileable(out.ctypes.data_as(ctypes.c_void_p), nx, ny, ctypes.c_float(sx), ctypes.c_float(sy), seed, ppt)
+    return out
+
+
+def run_positions_on_host(fn, text, pos, offsets, seed, workdir, tag):
+    dims = len(pos)
+    lib, ppt = build_on_host(fn, text, KIND_POS + dims, workdir, tag)
+    out = np.zeros(len(pos[0]), np.float32)
+    ptrs = [p.ctypes.data_as(ctypes.c_void_p) for p in pos] + [None] * (4 - dims)
+    lib.fn2_host_positions(out.ctypes.data_as(ctypes.c_void_p), dims, ctypes.c_longlong(len(pos[0])), *ptrs, (ctypes.c_float * dims)(*offsets), seed, ppt)
     return out
 
 
@@ -80,6 +103,19 @@ def test_generated_code_on_host_matches_oracle(fn, ref, flavour, tmp_path):
             if not same(got, want):
                 failures.append((name, dims, helpers.compare(got, want)))
     failures += fuzz(fn, ref, 12, 20260117, str(tmp_path), flavour.name)
+    # the other two entry kinds: torus mapping and scattered positions (ragged count: the tail path of the entry kernel)
+    rng = np.random.default_rng(7)
+    for name in ("c2_fbm5_perlin", "c4_terrain", "c5_supersimplex"):
+        node = helpers.RefNode(ref, fn.TREES[name])
+        got = run_tileable_on_host(fn, fn.TREES[name], 24, 10, 1.3, 0.9, 1337, str(tmp_path), "tile")
+        if not same(got, node.tileable2d(24, 10, 1.3, 0.9, 1337)[0]):
+            failures.append((name, "tileable"))
+        for dims in (2, 3, 4):
+            pos = [rng.uniform(-300, 300, 203).astype(np.float32) for _ in range(dims)]
+            offsets = [0.5, -1.5, 2.5, -3.5][:dims]
+            got = run_positions_on_host(fn, fn.TREES[name], pos, offsets, 1337, str(tmp_path), "pos")
+            if not same(got, node.positions(pos, offsets, 1337)[0]):
+                failures.append((name, "positions", dims))
     assert not failures, failures[:5]
 
 
