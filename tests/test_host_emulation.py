@@ -145,3 +145,21 @@ if __name__ == "__main__":
         print(label, "done,", len(bad), "mismatching (tree, dimension) pairs so far", flush=True)
     for item in bad[:20]:
         print(item)
+
+
+def test_smaller_points_per_thread_variants_on_host(fn, ref, tmp_path, monkeypatch):
+    """The 1- and 2-points-per-thread variants (what the library launches for row widths that 4 does not divide, and for
+    calls too small to fill the GPU) on odd grid sizes."""
+    failures = []
+    for ppt, n in (("1", (9, 7, 5)), ("2", (10, 7, 3))):
+        monkeypatch.setenv("FASTNOISE2_B200_PPT", ppt)
+        for name in ("c4_terrain", "c3a_cellular_distance"):
+            lib, got_ppt = build_on_host(fn, fn.TREES[name], 3, str(tmp_path), "ppt")
+            assert got_ppt == int(ppt)
+            out = np.zeros(int(np.prod(n)), np.float32)
+            lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), 3, (ctypes.c_float * 3)(0.5, -2.0, 3.0), (ctypes.c_int * 3)(*n),
+                              (ctypes.c_float * 3)(1.3, 1.1, 0.9), 7, got_ppt)
+            want = helpers.RefNode(ref, fn.TREES[name]).grid3d(0.5, -2.0, 3.0, *n, 1.3, 1.1, 0.9, 7)[0]
+            if not same(out, want):
+                failures.append((ppt, name, helpers.compare(out, want)))
+    assert not failures, failures
