@@ -18,7 +18,7 @@ namespace fn2
     // Vertex producers shared with DomainWarpSuperSimplex [DomainWarpSimplex.inl:1133-1833 repeats the geometry below],
     // vertices in the reference's accumulation order, falloff already raised to the 4th power.
     // [Simplex.inl:293-377]
-    template<class F>
+    template<int SCALE, class F>
     FN2_DI void supersimplex2_vertices( i32 seed, F x, F y, Verts2<F> ( &v )[4] )
     {
         typedef typename pack<F>::I I;
@@ -42,10 +42,10 @@ namespace fn2
         F dxBase = dxS + unskewDelta, dyBase = dyS + unskewDelta;
 
         F falloffBase0 = fnma_( dxBase, dxBase, fnma_( dyBase, dyBase, kR2 ) );
-        v[0] = { hash_hb( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
+        v[0] = { hash_hbs<SCALE>( seed, xP, yP ), dxBase, dyBase, pow4( falloffBase0 ) }; // vertex <0,0> (no clamp, as there)
         { // vertex <1,1>
             F falloff = fma_( unskewDelta, (float)( -4.0 * ( kRoot3 + 2.0 ) / ( kRoot3 + 3.0 ) ), falloffBase0 - kR2 );
-            v[1] = { hash_hb( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
+            v[1] = { hash_hbs<SCALE>( seed, iadd( xP, kPX ), iadd( yP, kPY ) ), dxBase - (float)( 2 * kUnskew2 + 1 ), dyBase - (float)( 2 * kUnskew2 + 1 ), pow4( falloff ) };
         }
 
         F xyDelta = select( forwardXY, F( (float)( kUnskew2 + 1 ) ), F( (float)( -kUnskew2 ) ) );
@@ -59,7 +59,7 @@ namespace fn2
             F dx = dxBase - ( select( forwardX, F( (float)( 1 + 2 * kUnskew2 ) ), F( -1.0f ) ));
             F dy = select( forwardX, dyBase - (float)( 2 * kUnskew2 ), dyBase );
             F falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            v[2] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
+            v[2] = { hash_hbs<SCALE>( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
         { // vertex <0,1> or <0,-1> or <2,1>
             I xv = select( forwardXY, iadd( xP, kPX ), xP );
@@ -68,7 +68,7 @@ namespace fn2
             F dx = select( forwardY, dxBase - (float)( 2 * kUnskew2 ), dxBase );
             F dy = dyBase - ( select( forwardY, F( (float)( 1 + 2 * kUnskew2 ) ), F( -1.0f ) ));
             F falloff = max_( fnma_( dx, dx, fnma_( dy, dy, kR2 ) ), 0.0f );
-            v[3] = { hash_hb( seed, xv, yv ), dx, dy, pow4( falloff ) };
+            v[3] = { hash_hbs<SCALE>( seed, xv, yv ), dx, dy, pow4( falloff ) };
         }
     }
 
@@ -78,7 +78,7 @@ namespace fn2
         typedef typename pack<F>::I I;
         typedef typename pack<F>::B B;
         Verts2<F> v[4];
-        supersimplex2_vertices( seed, x, y, v );
+        supersimplex2_vertices<kGradHashScale>( seed, x, y, v );
         F value = v[0].falloff * grad_dot2( v[0].hb, v[0].dx, v[0].dy );
 #pragma unroll
         for( int k = 1; k < 4; k++ ) value = fma_( v[k].falloff, grad_dot2( v[k].hb, v[k].dx, v[k].dy ), value );
@@ -86,7 +86,7 @@ namespace fn2
     }
 
     // [Simplex.inl:379-576]
-    template<class F>
+    template<int SCALE, class F>
     FN2_DI void supersimplex3_vertices( i32 seed, F x, F y, F z, Verts3<F> ( &v )[8] )
     {
         typedef typename pack<F>::I I;
@@ -145,56 +145,56 @@ namespace fn2
             F fb = fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            v[0] = { hash_hb( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
+            v[0] = { hash_hbs<SCALE>( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
         }
         { // <1,1,1> or <-1,-1,-1>
             B sm = xyzN < 0.0f;
             I sign = signbit_if( sm );
             F o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
             F fb = max_( fma_( o, coordSum, stemA ), 0.0f );
-            v[1] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
+            v[1] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
         }
         { // <1,1,0> or <-1,-1,0>
             B sm = xyzN < zN;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             F fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
-            v[2] = { hash_hb( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
+            v[2] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
         }
         { // <1,0,1> or <-1,0,-1>
             B sm = xyzN < yN;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             F fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
-            v[3] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
+            v[3] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
         }
         { // <0,1,1> or <0,-1,-1>
             B sm = xyzN < xN;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
             F fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
-            v[4] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
+            v[4] = { hash_hbs<SCALE>( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
         }
         { // <1,0,0> or <-1,0,0>
             B sm = xN < 0.0f;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)kReflectUnskew3, sign );
             F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
-            v[5] = { hash_hb( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
+            v[5] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
         }
         { // <0,1,0> or <0,-1,0>
             B sm = yN < 0.0f;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)kReflectUnskew3, sign );
             F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
-            v[6] = { hash_hb( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
+            v[6] = { hash_hbs<SCALE>( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
         }
         { // <0,0,1> or <0,0,-1>
             B sm = zN < 0.0f;
             I sign = signbit_if( sm );
             F o0 = fxor( (float)kReflectUnskew3, sign );
             F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
-            v[7] = { hash_hb( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
+            v[7] = { hash_hbs<SCALE>( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
         }
     }
 
@@ -204,7 +204,7 @@ namespace fn2
         typedef typename pack<F>::I I;
         typedef typename pack<F>::B B;
         Verts3<F> v[8];
-        supersimplex3_vertices( seed, x, y, z, v );
+        supersimplex3_vertices<kGradHashScale>( seed, x, y, z, v );
         F value = v[0].falloff * grad_dot3( v[0].hb, v[0].dx, v[0].dy, v[0].dz );
 #pragma unroll
         for( int k = 1; k < 8; k++ ) value = fma_( v[k].falloff, grad_dot3( v[k].hb, v[k].dx, v[k].dy, v[k].dz ), value );
@@ -212,7 +212,7 @@ namespace fn2
     }
 
     // [Simplex.inl:578-936]
-    template<class F>
+    template<int SCALE, class F>
     FN2_DI void supersimplex4_vertices( i32 seed, F x, F y, F z, F w, Verts4<F> ( &v )[16] )
     {
         typedef typename pack<F>::I I;
@@ -284,7 +284,7 @@ namespace fn2
             F fb = fnma_( dwB, dwB, fnma_( dzB, dzB, fnma_( dyB, dyB, fnma_( dxB, dxB, kR2 ) ) ) ) * 0.5f;
             stemA = fb - (float)( kDistanceSquaredA * 0.5 );
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
-            v[0] = { hash_hb( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
+            v[0] = { hash_hbs<SCALE>( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
         }
 
         // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many.
@@ -298,7 +298,7 @@ namespace fn2
             F o0 = fxor( (float)( K * kUnskew4 ), sign ); \
             (void)o0; \
             F fb = max_( FALLOFF, 0.0f ); \
-            v[SLOT] = { hash_hb( seed, select( MX, step_prime( xP, kPX, sm ), xP ), select( MY, step_prime( yP, kPY, sm ), yP ), select( \
+            v[SLOT] = { hash_hbs<SCALE>( seed, select( MX, step_prime( xP, kPX, sm ), xP ), select( MY, step_prime( yP, kPY, sm ), yP ), select( \
                                      MZ, step_prime( zP, kPZ, sm ), zP ), select( MW, step_prime( wP, kPW, sm ), wP )), \
                         dxB - ( select( MX, o1, o0 )), dyB - ( select( MY, o1, o0 )), dzB - ( select( MZ, o1, o0 )), dwB - ( select( MW, o1, o0 )), sq2( fb ) }; \
         }
@@ -327,7 +327,7 @@ namespace fn2
         typedef typename pack<F>::I I;
         typedef typename pack<F>::B B;
         Verts4<F> v[16];
-        supersimplex4_vertices( seed, x, y, z, w, v );
+        supersimplex4_vertices<kGradHashScale>( seed, x, y, z, w, v );
         F value = v[0].falloff * grad_dot4( v[0].hb, v[0].dx, v[0].dy, v[0].dz, v[0].dw );
 #pragma unroll
         for( int k = 1; k < 16; k++ ) value = fma_( v[k].falloff, grad_dot4( v[k].hb, v[k].dx, v[k].dy, v[k].dz, v[k].dw ), value );

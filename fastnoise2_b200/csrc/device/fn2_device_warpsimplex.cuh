@@ -296,14 +296,14 @@ namespace fn2
         if( LATTICE == 0 )
         {
             Verts2<float> v[3];
-            simplex2_vertices( seed, x, y, v );
+            simplex2_vertices<1>( seed, x, y, v );
 #pragma unroll
             for( int k = 0; k < 3; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
         }
         else
         {
             Verts2<float> v[4];
-            supersimplex2_vertices( seed, x, y, v );
+            supersimplex2_vertices<1>( seed, x, y, v );
 #pragma unroll
             for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].falloff, valueX, valueY );
         }
@@ -321,14 +321,14 @@ namespace fn2
         if( LATTICE == 0 )
         {
             Verts3<float> v[4];
-            simplex3_vertices( seed, x, y, z, v );
+            simplex3_vertices<1>( seed, x, y, z, v );
 #pragma unroll
             for( int k = 0; k < 4; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
         }
         else
         {
             Verts3<float> v[8];
-            supersimplex3_vertices( seed, x, y, z, v );
+            supersimplex3_vertices<1>( seed, x, y, z, v );
 #pragma unroll
             for( int k = 0; k < 8; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].falloff, valueX, valueY, valueZ );
         }
@@ -357,14 +357,14 @@ namespace fn2
         if( LATTICE == 0 )
         {
             Verts4<float> v[5];
-            simplex4_vertices( seed, x, y, z, w, v );
+            simplex4_vertices<1>( seed, x, y, z, w, v );
 #pragma unroll
             for( int k = 0; k < 5; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
         }
         else
         {
             Verts4<float> v[16];
-            supersimplex4_vertices( seed, x, y, z, w, v );
+            supersimplex4_vertices<1>( seed, x, y, z, w, v );
 #pragma unroll
             for( int k = 0; k < 16; k++ ) vec_contribution<SCHEME>( hash_fold( v[k].hb ), v[k].dx, v[k].dy, v[k].dz, v[k].dw, v[k].falloff, valueX, valueY, valueZ, valueW );
         }
