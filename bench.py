@@ -366,7 +366,7 @@ def main():
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json"))).get(args.workload, {})
         traffic = prof.get("dram_bytes_per_launch")
-        inst_per_point = prof.get("thread_inst_per_point") if args.math == "strict" else None
+        inst_per_point = prof.get("thread_inst_per_point") if args.math == "strict" and "stale" not in prof else None
         packed_per_point = prof.get("packed_thread_inst_per_point", 0.0) if inst_per_point else 0.0
     except (OSError, ValueError):
         pass
