@@ -388,7 +388,7 @@ def main():
                    "output_minmax": [lo, hi]},
         "roofline": {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak if peak and achieved else None, "issue_slot_frac": issue_frac,
                      "achieved_is": ("lane-operations per second = (%.1f thread-inst/point, of which %.1f packed FP32 counted twice; profiles/r1_ncu_summary.json, ncu) x points / kernel time" % (inst_per_point, packed_per_point)) if inst_per_point
-                     else "no ncu instruction count is committed for this workload + math mode (profiles/r1_ncu_summary.json): see reference_ops",
+                     else "no ncu instruction count of the current kernel is committed for this workload + math mode (profiles/r1_ncu_summary.json): see reference_ops",
                      "traffic": traffic, "traffic_source": "profiles/r1_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)" if traffic else None,
                      "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-specialised tree kernel)", "kernel_ms": kernel_ms,
                      "inst_per_point": inst_per_point,
