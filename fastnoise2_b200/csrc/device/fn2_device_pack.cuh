@@ -90,6 +90,8 @@ namespace fn2
     FN2_LANES1( fpair, round_, fpair )
     FN2_LANES2( fpair, min_, fpair, fpair )
     FN2_LANES2( fpair, max_, fpair, fpair )
+    FN2_LANES2( fpair, min_x86, fpair, fpair )
+    FN2_LANES2( fpair, max_x86, fpair, fpair )
     FN2_LANES1( fpair, sqrt_, fpair )
     FN2_LANES2( fpair, div_, fpair, fpair )
     FN2_LANES1( fpair, inv_sqrt, fpair )

@@ -159,6 +159,39 @@ namespace
             return !h.node && h.constant == value;
         }
 
+        // FS::Min / FS::Max with the reference's operand order. The one-instruction form (FMNMX) equals minps / maxps unless the
+        // second operand is NaN or the operands are zeros of opposite sign (fn2_device.cuh, min_x86): it is emitted when the
+        // second operand is a constant that rules both out, the compare + select form otherwise.
+        static bool ClampSafe( float second, bool isMax )
+        {
+            return second == second && !( second == 0.0f && std::signbit( second ) == isMax );
+        }
+        static bool HybClampSafe( const Generator* owner, int hybrid, bool isMax )
+        {
+            const Impl::NodeState::Hybrid& h = owner->State().hybrids[hybrid];
+            return !h.node && ClampSafe( h.constant, isMax );
+        }
+        static std::string MinMax( bool isMax, const std::string& first, const std::string& second, bool safe )
+        {
+            return std::string( isMax ? "fn2::max_" : "fn2::min_" ) + ( safe ? "( " : "x86( " ) + first + ", " + second + " )";
+        }
+
+        // Can this node return only finite values or NaN, never +-inf? True for the lattice and hash leaves with a sane output
+        // range: their native value is bounded for every input (a non-finite position turns into NaN inside them).
+        // Used by the fractals: Lerp( 1, t, 0 ) is 1 for every finite t and NaN for an infinite one.
+        static bool FiniteOrNaN( const Generator* node )
+        {
+            if( !node ) return false;
+            const Impl::NodeState& s = node->State();
+            switch( s.nodeId )
+            {
+            case N_Perlin: case N_Simplex: case N_SuperSimplex: case N_Value: case N_White: case N_Checkerboard: case N_SineWave: case N_CellularValue:
+                return std::fabs( s.f[F_RangeScale] ) < 0x1p100f && std::fabs( s.f[F_RangeMin] ) < 0x1p100f;
+            default:
+                return false;
+            }
+        }
+
         // ScaleOutput [BasicGenerators.inl:27-30]: fma( (1/(max-min)) * rangeScale, value - min, rangeMin ), factor folded on the host in float
         static std::string Range( const Impl::NodeState& s, const std::string& value, float nativeMin, float nativeMax )
         {
@@ -371,7 +404,9 @@ namespace
             case N_FractalRidged: // [Fractal.inl:44-66]
             {
                 const bool ridged = s.nodeId == N_FractalRidged;
-                const bool weighted = !HybIsConst( g, 1, 0.0f );
+                // with a constant weighted strength of 0 the factor is fma( 0, t - 1, 1 ): 1 for every finite t, NaN when the
+                // source returned +-inf (then the reference's sum ends as NaN, not inf) -- skipped only over sources that cannot
+                const bool weighted = !( HybIsConst( g, 1, 0.0f ) && FiniteOrNaN( g->State().lookups[0].get() ) );
                 int octaves = s.i[I_K0];
                 std::string sample = Src( g, 0, dim, "seed", P );
                 if( ridged ) sample = "fn2::abs_( " + sample + " )";
@@ -384,7 +419,6 @@ namespace
                 {
                     b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
                     b << "        seed = fn2::iadd( seed, 1 );\n";
-                    // with a constant weighted strength of 0 the factor is fma( 0, t - 1, 1 ) == 1 for every finite t
                     if( weighted ) b << "        amp *= fn2::lerp( 1.0f, " << ( ridged ? "1.0f - noise" : "( noise + 1.0f ) * 0.5f" ) << ", weightedStrength );\n";
                     b << "        amp *= gain;\n";
                     for( int d = 0; d < dim; d++ ) b << "        " << kAxis[d] << " *= " << Lit( s.f[F_K0] ) << ";\n";
@@ -461,10 +495,10 @@ namespace
                 b << "    return " << Src( g, 0, dim, "seed", P ) << " * " << Hyb( g, 0, dim, "seed", P ) << ";\n";
                 break;
             case N_Min:
-                b << "    return fn2::min_( " << Src( g, 0, dim, "seed", P ) << ", " << Hyb( g, 0, dim, "seed", P ) << " );\n";
+                b << "    return " << MinMax( false, Src( g, 0, dim, "seed", P ), Hyb( g, 0, dim, "seed", P ), HybClampSafe( g, 0, false ) ) << ";\n";
                 break;
             case N_Max:
-                b << "    return fn2::max_( " << Src( g, 0, dim, "seed", P ) << ", " << Hyb( g, 0, dim, "seed", P ) << " );\n";
+                b << "    return " << MinMax( true, Src( g, 0, dim, "seed", P ), Hyb( g, 0, dim, "seed", P ), HybClampSafe( g, 0, true ) ) << ";\n";
                 break;
             case N_Subtract:
                 b << "    return " << Hyb( g, 0, dim, "seed", P ) << " - " << Hyb( g, 1, dim, "seed", P ) << ";\n";
@@ -491,10 +525,11 @@ namespace
                 const char* neg = s.nodeId == N_MaxSmooth ? "-" : "";
                 b << "    const F a = " << neg << Src( g, 0, dim, "seed", P ) << ";\n";
                 b << "    const F b = " << neg << Hyb( g, 0, dim, "seed", P ) << ";\n";
-                b << "    const F smoothness = fn2::max_( 0x1p-126f, fn2::abs_( " << Hyb( g, 1, dim, "seed", P ) << " ) );\n";
+                // |smoothness| is +0 or larger: only a NaN can make the two forms differ
+                b << "    const F smoothness = " << MinMax( true, "0x1p-126f", "fn2::abs_( " + Hyb( g, 1, dim, "seed", P ) + " )", HybClampSafe( g, 1, false ) && HybClampSafe( g, 1, true ) ) << ";\n";
                 b << "    F h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
                 b << "    h *= fn2::reciprocal( smoothness );\n";
-                b << "    return " << neg << "fn2::fnma_( " << Lit( 1.0f / 6.0f ) << ", h * h * h * smoothness, fn2::min_( a, b ) );\n";
+                b << "    return " << neg << "fn2::fnma_( " << Lit( 1.0f / 6.0f ) << ", h * h * h * smoothness, " << MinMax( false, "a", "b", HybClampSafe( g, 0, false ) && HybClampSafe( g, 0, true ) ) << " );\n";
                 break;
             }
 
@@ -565,8 +600,8 @@ namespace
             {
                 const float lo = s.f[F_K0], hi = s.f[F_K0 + 1];
                 b << "    F v = " << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    v = fn2::min_( v, " << Lit( hi ) << " );\n";
-                b << "    v = fn2::max_( v, " << Lit( lo ) << " );\n";
+                b << "    v = " << MinMax( false, "v", Lit( hi ), ClampSafe( hi, false ) ) << ";\n";
+                b << "    v = " << MinMax( true, "v", Lit( lo ), ClampSafe( lo, true ) ) << ";\n";
                 b << "    v -= " << Lit( lo ) << ";\n";
                 b << "    v *= " << Lit( 255.0f / ( hi - lo ) ) << ";\n";
                 b << "    const I byteVal = fn2::cvt_i( v );\n";
@@ -585,7 +620,7 @@ namespace
                 b << "    const F fadeMax = " << Hyb( g, 2, dim, "seed", P ) << ";\n";
                 b << "    const F fadeRange = fadeMax - fadeMin;\n";
                 b << "    fade = fn2::div_( fade - fadeMin, fadeRange );\n";
-                b << "    fade = fn2::max_( 0.0f, fn2::min_( 1.0f, fade ) );\n";
+                b << "    fade = fn2::max_x86( 0.0f, fn2::min_x86( 1.0f, fade ) );\n";
                 if( s.i[I_K0] == 1 ) b << "    fade = fn2::hermite( fade );\n";
                 if( s.i[I_K0] == 2 ) b << "    fade = fn2::quintic( fade );\n";
                 b << "    fade = fn2::select( fadeRange == 0.0f, F( 0.5f ), fade );\n";
@@ -602,8 +637,8 @@ namespace
                 b << "    F result = toMin + ( fn2::div_( source - fromMin, fromMax - fromMin ) * ( toMax - toMin ) );\n";
                 if( s.i[I_K0] == 1 )
                 {
-                    b << "    result = fn2::max_( result, toMin );\n";
-                    b << "    result = fn2::min_( result, toMax );\n";
+                    b << "    result = " << MinMax( true, "result", "toMin", HybClampSafe( g, 2, true ) ) << ";\n";
+                    b << "    result = " << MinMax( false, "result", "toMax", HybClampSafe( g, 3, false ) ) << ";\n";
                 }
                 b << "    return result;\n";
                 break;

@@ -9,6 +9,15 @@ DEMO_TREES = {
     "cellular_caves": "FgIcCS4AAQ@BklCQs@BlRBDNzMw9G@AIMAgAw@ADgC@BCiQIzczMPgkJ@BPkIQH4XrPhjNzEw/DBIkCM3MzD4JCQ@ADBCCAE@BQzczMvhg@B/JAL/BAAL7FE4PgQKFwkNCQg@CQQQDuB4FPwt7FC4/BAOPwnU8DA==",
 }
 
+# Trees whose nodes produce NaN / inf / signed zeros at ordinary positions (found by the offline host-emulation fuzz): they pin the
+# minps / maxps operand convention of Min, Max, MaxSmooth ... and the fractals' weighted-strength factor over an infinite source.
+NON_FINITE_TREES = {
+    "max_of_perlin_and_modulus_by_zero": "GwkICP0AAAAYlU2YvwQCLQL/AAAM",                       # Max( Perlin, Modulus( Perlin, 0 ) ): NaN second operand
+    "ridged_over_divide_by_zero": "Dwgs/8U/CRgCGQkCAA0zxUEIuq5OvxCyXKG/FAO+2a0+BA==",         # FractalRidged( Divide( Abs( Checkerboard ), 0 ) ): inf source
+    "maxsmooth_with_modulus_by_zero": "FgIdCRYCCiABAAAAAzC6P0ALSg/PPgwCLQIEABSeb78IheUQvxB5Puc+GKI0ML8Dzc3XvxvKYShAHA==",
+    "nested_blends_with_signed_zeros": "KAACAAAAER8CFQkHAJzo+0EIFAAAABCtlkI+GNOPob8EA5a61j4EC8IoTz8EAAQCLQIKGODqZ78gAQAAACgAAAAAAgkAyBgQQQgSAAAAEO2s1z4Y1GczPwQTpzEgPgQKKgkBACf8//8I3hmEPxAYotE+BAPCTD0+DAtF6VG9EzV7Kz4E",
+}
+
 # checksums of the survey's prototype strict oracle (scalar 4-lane, libm) -- an independent
 # build of the same semantics. call = (kind, args): grid3d 64^3 step 4, grid2d 512^2 step 1, grid4d 32,32,16,16 step 4; seed 1337
 SURVEY_SMOKE = {

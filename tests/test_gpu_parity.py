@@ -379,6 +379,21 @@ def test_random_trees_vs_strict_oracle(gpu, ref):
     assert not failures, failures[:5]
 
 
+def test_non_finite_values_inside_a_tree_follow_the_x86_oracle(gpu, ref):
+    """Divide / Modulus by zero feed NaN and inf into Min, Max, MaxSmooth and a fractal: the oracle's minps / maxps operand
+    convention and its NaN weighted-strength factor decide the output (tests/cases.py NON_FINITE_TREES)."""
+    from tests.cases import NON_FINITE_TREES
+    from tests.fuzz import same
+    failures = []
+    for name, text in NON_FINITE_TREES.items():
+        a, b = helpers.ProductNode(gpu, text), helpers.RefNode(ref, text)
+        for dim, got, want in ((2, a.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, 146)[0], b.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, 146)[0]),
+                               (3, a.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, 146)[0], b.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, 146)[0])):
+            if not same(got, want):
+                failures.append((name, dim, helpers.compare(got, want)))
+    assert not failures, failures
+
+
 def test_concurrent_calls_from_threads(gpu):
     """The reference's Gen* methods are const and thread-safe; here every calling thread owns its streams, staging buffers
     and min/max accumulator. Eight threads hammer two shared generators (host and device destinations, first use compiles

@@ -80,6 +80,19 @@ def oracle_values(node, dims, seed):
     return call(*g["off"], *g["n"], *g["step"], seed)[0]
 
 
+def test_non_finite_values_follow_the_x86_oracle_on_host(fn, ref, flavour, tmp_path):
+    """NaN / inf / signed zeros produced INSIDE a tree take the oracle's path through Min / Max / MaxSmooth / the fractals."""
+    from tests.cases import NON_FINITE_TREES
+    failures = []
+    for name, text in NON_FINITE_TREES.items():
+        for dims in (2, 3):
+            got = run_on_host(fn, text, dims, 146, str(tmp_path), "nonfinite")
+            want = oracle_values(helpers.RefNode(ref, text), dims, 146)
+            if not same(got, want):
+                failures.append((name, dims, helpers.compare(got, want)))
+    assert not failures, failures
+
+
 def fuzz(fn, ref_lib, count, seed, workdir, label):
     fuzzer = TreeFuzzer(seed)
     failures = []
@@ -138,10 +151,11 @@ if __name__ == "__main__":
     import tempfile
     import fastnoise2_b200 as product
     total = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    base = int(sys.argv[2]) if len(sys.argv) > 2 else 9000  # fuzzer seed: run several processes with different bases in parallel
     bad = []
     for variant, mode, label in (("strict_avx512", 0, "tables"), ("strict_avx2", 2, "generic")):
         product.set_math_mode(mode)
-        bad += fuzz(product, helpers.load_ref(variant), total, 9000 + mode, tempfile.mkdtemp(), label)
+        bad += fuzz(product, helpers.load_ref(variant), total, base + mode, tempfile.mkdtemp(), label)
         print(label, "done,", len(bad), "mismatching (tree, dimension) pairs so far", flush=True)
     for item in bad[:20]:
         print(item)

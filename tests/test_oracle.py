@@ -117,3 +117,13 @@ def test_random_trees_port_vs_strict_ref(ref, port):
             if not same(got, want):
                 failures.append((index, dim, text, helpers.compare(got, want)))
     assert not failures, failures[:5]
+
+
+def test_port_oracle_non_finite_trees_vs_strict_ref(ref, port):
+    """NaN / inf / signed zeros born inside a tree (tests/cases.py NON_FINITE_TREES): both oracles take the minps / maxps path."""
+    from tests.cases import NON_FINITE_TREES
+    from tests.fuzz import same
+    for name, text in NON_FINITE_TREES.items():
+        a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
+        assert same(a.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, 146)[0], b.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, 146)[0]), name
+        assert same(a.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 146)[0], b.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 146)[0]), name
