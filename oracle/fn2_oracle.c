@@ -9,7 +9,8 @@
  *
  * Arithmetic contract = the STRICT semantics of oracle/shim (the stand-in for the absent FastSIMD dependency,
  * Auburn/FastSIMD @ 16450dae9528727e500e7254f635a671f9c7ee2d): IEEE single ops, fmaf exactly where the reference has
- * FS::FMulAdd/FNMulAdd/FMulSub, Convert<int> = cvtps2dq (round-to-nearest-even, 0x80000000 when out of range),
+ * FS::FMulAdd/FNMulAdd/FMulSub, Convert<int> = cvtps2dq (round-to-nearest-even, 0x80000000 when out of range;
+ * fn2oSetConvertMode( 1 ) switches to the saturating conversion of ARM / GPU builds for tests of that regime),
  * InvSqrt = 1/sqrt, and BOTH gradient flavours of the reference (fn2oSetFlavor: 0 = generic select/xor code paths,
  * 1 = the AVX512_F permute-table code paths). Pinned by tests/test_oracle.py against tests/golden/ (vectors produced
  * by the reference's own sources compiled over that shim, one set per flavour) and against those sources directly on
@@ -367,7 +368,17 @@ static i32 f2b( float v ) { i32 b; memcpy( &b, &v, 4 ); return b; }
 static float b2f( i32 b ) { float v; memcpy( &v, &b, 4 ); return v; }
 static float fxor( float v, i32 bits ) { return b2f( f2b( v ) ^ bits ); }
 /* FS::Convert<int32_t> = cvtps2dq: round to nearest even; NaN and anything outside [-2^31, 2^31) give the "integer indefinite" 0x80000000 */
-static i32 cvt_i( float v ) { return ( v >= -2147483648.0f && v < 2147483648.0f ) ? (i32)lrintf( v ) : (i32)0x80000000u; }
+/* fn2oSetConvertMode( 1 ): the SATURATING conversion of ISAs without an "indefinite" value (ARM fcvtns, the GPU's cvt.rni.s32.f32):
+ * NaN -> 0, too large -> INT_MAX, too small -> INT_MIN. The reference's result for such positions (beyond +-2^31 cells, or NaN)
+ * depends on the ISA it was built for; the tests use mode 1 to pin the product there too. Mode 0 (default) = x86. */
+static int gSaturatingConvert = 0;
+void fn2oSetConvertMode( int saturating ) { gSaturatingConvert = saturating != 0; }
+static i32 cvt_i( float v )
+{
+    if( v >= -2147483648.0f && v < 2147483648.0f ) return (i32)lrintf( v );
+    if( !gSaturatingConvert ) return (i32)0x80000000u;
+    return v != v ? 0 : ( v > 0.0f ? 0x7fffffff : (i32)0x80000000u );
+}
 static float fmin_x86( float a, float b ) { return a < b ? a : b; } /* minps operand order */
 static float fmax_x86( float a, float b ) { return a > b ? a : b; }
 static float fnma( float a, float b, float c ) { return fmaf( -a, b, c ); }

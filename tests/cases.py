@@ -18,6 +18,17 @@ NON_FINITE_TREES = {
     "nested_blends_with_signed_zeros": "KAACAAAAER8CFQkHAJzo+0EIFAAAABCtlkI+GNOPob8EA5a61j4EC8IoTz8EAAQCLQIKGODqZ78gAQAAACgAAAAAAgkAyBgQQQgSAAAAEO2s1z4Y1GczPwQTpzEgPgQKKgkBACf8//8I3hmEPxAYotE+BAPCTD0+DAtF6VG9EzV7Kz4E",
 }
 
+# Trees that reach Convert<int> with a value outside [-2^31, 2^31) on FAR_GRID_4D (found by the offline fuzz on a grid far from the
+# origin): x86 returns the "integer indefinite" there, the product saturates like ARM / the GPU's own conversion; the C port's
+# fn2oSetConvertMode( 1 ) is the oracle for that regime. (seed, encoded tree)
+FAR_GRID_4D = dict(off=(-91234.5, 70001.25, -333.0, 1e6), n=(4, 5, 3, 3), step=(37.7, 53.1, 0.5, 1024.0))
+CONVERT_OVERFLOW_TREES = [
+    (114, 'EAg3AAAAEH0ehz8gGCwxPzABAAAACSIJCAAGHvtBEBrfmr4EChYCBQN9VdQ/E5yijD8bu/fNPyOMEzBABAt6274/BBN/Gas/DA=='),
+    (47, 'IgkpAAEAAAAJCwjUAgAAEHL5OL4gBAAAACgAAAAAMAIAAAA4AQAAAAIGACQEFUIIMQAAABBJtQQ+GGf7LD8EC/OJvj4TUH6qPQQDQpYSPwoJCMYAAAAEE8QuAr8bOf52PwQCBQL/AgALgrjoPhIuAAEAAAAJAggb9Ri/EO2I+78MI+0y9j8ECikAAAAAAAkkALU22T8InjuKPxiZmxJACQUABQAAAAthPAdAGxQvoT8MA5PKnT8LB7smPxNlyi2/BBIsAAMAAAAJBQAAAAAAAgcA2NEwQQhh////EPNfsL4YZAZ8vgQLZ+49QBuwfVtAI+OHnD8U'),
+    (5, 'IgkUAAMAAAAIEHIeQAkRAG1mVkII1gEAADABAAAACQIA4ywgQghoecM/DAIIACLgeUEIEQAAABDKPuA9GDTCdz4MAwFvhEATsx4VQBoVCQ8AAgAAAAgeCwNACQQAZOW7PhAYKum9GOvbGz8blFmbPwQCCAAbzwBBCCsAAAAQmDPdPRhuRAI/BAshg0Y+FA=='),
+    (100, 'JQkFAgwAyxD2QQiT/f//EAQAAAAJCABZzQ5CCKEAAAAQnjz/PxjPHeM/BAshFSE/BBIQAIyhvUEIqf///xAwYiY/GG7avT8JCgA0fQVCGIHphT8gBQAAACgCAAAAC1RUFT8TFEi5PgQCBQO/iIc/CwRyQkATwPYKvxvqBeG/IwtoF0AMG3a4lD8M'),
+]
+
 # checksums of the survey's prototype strict oracle (scalar 4-lane, libm) -- an independent
 # build of the same semantics. call = (kind, args): grid3d 64^3 step 4, grid2d 512^2 step 1, grid4d 32,32,16,16 step 4; seed 1337
 SURVEY_SMOKE = {

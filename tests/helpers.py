@@ -154,6 +154,7 @@ def load_port():
     lib.fn2oDecode.argtypes = [ctypes.c_char_p]
     lib.fn2oFree.argtypes = [P]
     lib.fn2oSupported.argtypes = [P]
+    lib.fn2oSetConvertMode.argtypes = [I]
     lib.fn2oNodeId.argtypes = [P]
     lib.fn2oGrid.argtypes = [P, P, I, P, P, P, I, LL, LL, P]
     lib.fn2oTileable.argtypes = [P, P, I, I, F, F, I, I, I, P]

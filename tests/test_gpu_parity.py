@@ -394,6 +394,22 @@ def test_non_finite_values_inside_a_tree_follow_the_x86_oracle(gpu, ref):
     assert not failures, failures
 
 
+def test_convert_overflow_regime_matches_the_saturating_port(gpu, port):
+    """Positions whose cell coordinates leave the int32 range: x86 builds of the reference produce the "integer indefinite",
+    this implementation saturates (like ARM builds); the C restatement switched to saturating conversion is the oracle."""
+    from tests.cases import CONVERT_OVERFLOW_TREES, FAR_GRID_4D
+    from tests.fuzz import same
+    g = FAR_GRID_4D
+    port.fn2oSetConvertMode(1)
+    try:
+        for seed, text in CONVERT_OVERFLOW_TREES:
+            got = helpers.ProductNode(gpu, text).grid4d(*g["off"], *g["n"], *g["step"], seed)[0]
+            want = helpers.PortNode(port, text).grid4d(*g["off"], *g["n"], *g["step"], seed)[0]
+            assert same(got, want), (text, helpers.compare(got, want))
+    finally:
+        port.fn2oSetConvertMode(0)
+
+
 def test_concurrent_calls_from_threads(gpu):
     """The reference's Gen* methods are const and thread-safe; here every calling thread owns its streams, staging buffers
     and min/max accumulator. Eight threads hammer two shared generators (host and device destinations, first use compiles

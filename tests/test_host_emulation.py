@@ -93,11 +93,24 @@ def test_non_finite_values_follow_the_x86_oracle_on_host(fn, ref, flavour, tmp_p
     assert not failures, failures
 
 
-def fuzz(fn, ref_lib, count, seed, workdir, label):
+def test_convert_overflow_regime_matches_the_saturating_port_on_host(fn, port, flavour, tmp_path, monkeypatch):
+    """Cell coordinates beyond +-2^31: the product's Convert<int> saturates; the C restatement in its saturating mode is the oracle."""
+    from tests.cases import CONVERT_OVERFLOW_TREES, FAR_GRID_4D
+    monkeypatch.setitem(GRIDS, 4, FAR_GRID_4D)
+    port.fn2oSetConvertMode(1)
+    try:
+        for seed, text in CONVERT_OVERFLOW_TREES:
+            got = run_on_host(fn, text, 4, seed, str(tmp_path), "overflow")
+            assert same(got, oracle_values(helpers.PortNode(port, text), 4, seed)), text
+    finally:
+        port.fn2oSetConvertMode(0)
+
+
+def fuzz(fn, ref_lib, count, seed, workdir, label, depth=3):
     fuzzer = TreeFuzzer(seed)
     failures = []
     for index in range(count):
-        text = fuzzer.tree(depth=3).encode()
+        text = fuzzer.tree(depth=depth).encode()
         for dims in (2, 3, 4):
             got = run_on_host(fn, text, dims, index, workdir, "%s_%d" % (label, dims))
             want = oracle_values(helpers.RefNode(ref_lib, text), dims, index)
@@ -152,10 +165,15 @@ if __name__ == "__main__":
     import fastnoise2_b200 as product
     total = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     base = int(sys.argv[2]) if len(sys.argv) > 2 else 9000  # fuzzer seed: run several processes with different bases in parallel
+    depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    if os.environ.get("FN2_FUZZ_GRIDS") == "far":               # far from the origin, negative, coarse: big cell coordinates
+        GRIDS.update({2: dict(off=(-91234.5, 70001.25), n=(20, 13), step=(37.7, 53.1)),
+                      3: dict(off=(-91234.5, 70001.25, -333.0), n=(8, 7, 5), step=(37.7, 53.1, 0.5)),
+                      4: dict(off=(-91234.5, 70001.25, -333.0, 1e6), n=(4, 5, 3, 3), step=(37.7, 53.1, 0.5, 1024.0))})
     bad = []
     for variant, mode, label in (("strict_avx512", 0, "tables"), ("strict_avx2", 2, "generic")):
         product.set_math_mode(mode)
-        bad += fuzz(product, helpers.load_ref(variant), total, base + mode, tempfile.mkdtemp(), label)
+        bad += fuzz(product, helpers.load_ref(variant), total, base + mode, tempfile.mkdtemp(), label, depth)
         print(label, "done,", len(bad), "mismatching (tree, dimension) pairs so far", flush=True)
     for item in bad[:20]:
         print(item)
