@@ -4,7 +4,10 @@ values must equal the strict oracle's bit for bit. This exercises the emitter an
 the node library for random trees without a GPU. It is a test harness around product-generated code, not a product path:
 nothing under fastnoise2_b200/ can evaluate noise on the CPU.
 
-    python tests/test_host_emulation.py 2000        # offline fuzz with that many random trees per flavour
+    python tests/test_host_emulation.py 2000 [seed base] [tree depth]   # offline fuzz with that many random trees per flavour
+    FN2_FUZZ_GRIDS=far ...      grids far from the origin (big cell coordinates; Convert<int> overflow shows up in 4D)
+    FN2_FUZZ_ENTRIES=1 ...      every tree also through the tileable and position-array entry kernels
+    FASTNOISE2_B200_PACK=2 FASTNOISE2_B200_FILL=0 ...   the packed-FP32 form
 """
 import ctypes
 import os
@@ -116,6 +119,16 @@ def fuzz(fn, ref_lib, count, seed, workdir, label, depth=3):
             want = oracle_values(helpers.RefNode(ref_lib, text), dims, index)
             if not same(got, want):
                 failures.append((label, index, dims, text, helpers.compare(got, want)))
+        if os.environ.get("FN2_FUZZ_ENTRIES"):          # offline runs: also the torus mapping and a ragged position array
+            node = helpers.RefNode(ref_lib, text)
+            got = run_tileable_on_host(fn, text, 12, 7, 1.3, 0.9, index, workdir, label + "_tile")
+            if not same(got, node.tileable2d(12, 7, 1.3, 0.9, index)[0]):
+                failures.append((label, index, "tileable", text, {}))
+            rng = np.random.default_rng(index)
+            pos = [rng.uniform(-300, 300, 203).astype(np.float32) for _ in range(3)]
+            got = run_positions_on_host(fn, text, pos, [0.5, -1.5, 2.5], index, workdir, label + "_pos")
+            if not same(got, node.positions(pos, [0.5, -1.5, 2.5], index)[0]):
+                failures.append((label, index, "positions3d", text, {}))
     return failures
 
 
