@@ -39,7 +39,7 @@ namespace
         }
         else if( std::isinf( v ) )
         {
-            std::snprintf( buf, sizeof( buf ), "%sFN2_INF", v < 0 ? "-" : "" );
+            std::snprintf( buf, sizeof( buf ), v < 0 ? "(-FN2_INF)" : "FN2_INF" );
         }
         else
         {
