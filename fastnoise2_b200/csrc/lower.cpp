@@ -361,7 +361,9 @@ namespace
             {
                 bool sizeJ = cellularPrologue( true );
                 int df = s.i[I_K0];
-                if( df < 0 || df > 5 ) df = 0;
+                // an out-of-range distance function enters CalcDistance<false> at `default:` and falls through to the
+                // EuclideanSquared case [Utils.inl:286-302], and GetReturn's Euclidean test fails [Cellular.inl:533]
+                if( df < 0 || df > 5 ) df = 1;
                 int i0 = s.i[I_K0 + 1], i1 = s.i[I_K0 + 2], ret = s.i[I_K0 + 3];
                 if( ret < 0 || ret > 4 ) ret = 0;
                 int top = ( df == 0 || ret != 0 ) ? std::max( i0, i1 ) : i0;
@@ -696,6 +698,12 @@ namespace
             case N_DomainRotatePlane: // [Modifiers.inl:352-409]
             {
                 bool xz = dim != 2 && s.i[I_K0] == 1; // 2D input always uses the XY preset
+                if( dim != 2 && s.i[I_K0] != 0 && s.i[I_K0] != 1 )
+                {
+                    // an out-of-range rotation type falls through the reference's switch: the coordinates pass unchanged
+                    b << "    return " << Src( g, 0, dim, "seed", P ) << ";\n";
+                    break;
+                }
                 if( dim == 2 ) b << "    const F z = 0.0f;\n";
                 const char* A = xz ? "z" : "y"; // the axis paired with x
                 const char* B = xz ? "y" : "z"; // the axis that is "improved away"

@@ -1428,6 +1428,7 @@ static float eval( const Node* n, i32 seed, int dim, const float* pin )
     case N_DomainRotatePlane: /* :352-409 */
     {
         int xz = dim != 2 && n->i[0] == 1;
+        if( dim != 2 && n->i[0] != 0 && n->i[0] != 1 ) return eval( src, seed, dim, p ); /* no case of the switch [:361-388]: unchanged */
         float x = p[0], y = p[1], z = dim == 2 ? 0.0f : p[2], q[4];
         float a = xz ? z : y, b = xz ? y : z;
         float pair = x + a, s2 = pair * -0.211324865405187f, nb = b * 0.577350269189626f;

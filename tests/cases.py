@@ -29,6 +29,28 @@ CONVERT_OVERFLOW_TREES = [
     (100, 'JQkFAgwAyxD2QQiT/f//EAQAAAAJCABZzQ5CCKEAAAAQnjz/PxjPHeM/BAshFSE/BBIQAIyhvUEIqf///xAwYiY/GG7avT8JCgA0fQVCGIHphT8gBQAAACgCAAAAC1RUFT8TFEi5PgQCBQO/iIc/CwRyQkATwPYKvxvqBeG/IwtoF0AMG3a4lD8M'),
 ]
 
+
+
+def out_of_range_enum_trees():
+    """Enum members written with values outside their range (every setter and the decoder accept any int): the reference's
+    switch statements decide -- `default:` labels, fall-throughs, or no case at all. name -> encoded tree"""
+    from tests.encode import N
+    simplex = lambda: N("Simplex", {"Feature Scale": 23.0})
+    return {
+        "cellular_distance_function_-1": N("CellularDistance", {"Distance Function": -1, "Feature Scale": 11.0}).encode(),    # EuclideanSquared without the final sqrt
+        "cellular_distance_function_9_return_7": N("CellularDistance", {"Distance Function": 9, "Return Type": 7, "Distance Index 1": 2}).encode(),
+        "cellular_value_function_6": N("CellularValue", {"Distance Function": 6, "Value Index": 1}).encode(),
+        "cellular_lookup_function_-3": N("CellularLookup", {"Distance Function": -3}, [simplex()]).encode(),
+        "distance_to_point_function_8": N("DistanceToPoint", {"Distance Function": 8}, [], {("Point", 0): 3.5}).encode(),   # Euclidean with sqrt
+        "rotate_plane_type_-1": N("DomainRotatePlane", {"Rotation Type": -1}, [simplex()]).encode(),                         # coordinates pass unchanged
+        "rotate_plane_type_2": N("DomainRotatePlane", {"Rotation Type": 2}, [simplex()]).encode(),
+        "fade_interpolation_5": N("Fade", {"Interpolation": 5}, [simplex(), N("Perlin")], {"Fade": N("Value", {"Feature Scale": 9.0})}).encode(),
+        "warp_simplex_scheme_4": N("DomainWarpSimplex", {"Vectorization Scheme": 4}, [simplex()]).encode(),
+        "remove_dimension_6": N("RemoveDimension", {"Remove Dimension": 6}, [simplex()]).encode(),
+        "pow_int_-2": N("PowInt", {"Pow": -2}, [simplex()]).encode(),
+    }
+
+
 # SURVEY.md section 8(c): checksums of the survey's prototype strict oracle (scalar 4-lane, libm) -- an independent
 # build of the same semantics. call = (kind, args): grid3d 64^3 step 4, grid2d 512^2 step 1, grid4d 32,32,16,16 step 4; seed 1337
 SURVEY_SMOKE = {

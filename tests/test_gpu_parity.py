@@ -394,6 +394,22 @@ def test_non_finite_values_inside_a_tree_follow_the_x86_oracle(gpu, ref):
     assert not failures, failures
 
 
+def test_out_of_range_enum_values_follow_the_reference_switches(gpu, ref):
+    """Enum members written outside their range (setters and decoder accept any int) take the reference's `default:` label,
+    fall-through or no-case path (tests/cases.py out_of_range_enum_trees)."""
+    from tests.cases import out_of_range_enum_trees
+    from tests.fuzz import same
+    failures = []
+    for name, text in out_of_range_enum_trees().items():
+        a, b = helpers.ProductNode(gpu, text), helpers.RefNode(ref, text)
+        for dim, got, want in ((2, a.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, 31)[0], b.grid2d(-3.3, 2.1, 48, 40, 1.9, 1.7, 31)[0]),
+                               (3, a.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, 31)[0], b.grid3d(-3.3, 2.1, 0.7, 16, 14, 12, 1.9, 1.7, 2.3, 31)[0]),
+                               (4, a.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, 31)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 8, 7, 6, 5, 1.9, 1.7, 2.3, 1.1, 31)[0])):
+            if not same(got, want):
+                failures.append((name, dim, helpers.compare(got, want)))
+    assert not failures, failures
+
+
 def test_convert_overflow_regime_matches_the_saturating_port(gpu, port):
     """Positions whose cell coordinates leave the int32 range: x86 builds of the reference produce the "integer indefinite",
     this implementation saturates (like ARM builds); the C restatement switched to saturating conversion is the oracle."""

@@ -127,3 +127,14 @@ def test_port_oracle_non_finite_trees_vs_strict_ref(ref, port):
         a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
         assert same(a.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, 146)[0], b.grid2d(-3.3, 2.1, 24, 24, 1.9, 1.7, 146)[0]), name
         assert same(a.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 146)[0], b.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 146)[0]), name
+
+
+def test_port_oracle_out_of_range_enums_vs_strict_ref(ref, port):
+    """Enum members outside their range (tests/cases.py out_of_range_enum_trees): the restatement takes the same switch paths."""
+    from tests.cases import out_of_range_enum_trees
+    from tests.fuzz import same
+    for name, text in out_of_range_enum_trees().items():
+        a, b = helpers.PortNode(port, text), helpers.RefNode(ref, text)
+        assert a.supported, name
+        assert same(a.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 31)[0], b.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 31)[0]), name
+        assert same(a.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, 31)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, 31)[0]), name
