@@ -23,12 +23,22 @@ HYBRID_RANGES = {
 
 
 class TreeFuzzer:
-    def __init__(self, seed):
+    def __init__(self, seed, wild=0.0):
+        """wild: probability that a float parameter leaves its sensible range (zero, negative, tiny, large) and an int / enum
+        member its valid one -- the trees then produce NaN, inf and signed zeros, which must follow the oracle all the same."""
         self.rng = np.random.default_rng(seed)
         self.pool = []      # finished sub-trees that may be shared
+        self.wild = wild
 
     def uniform(self, lo, hi):
+        if self.wild and self.rng.random() < self.wild:
+            return float(np.float32(self.rng.choice([0.0, -0.0, -self.rng.uniform(lo, hi) if lo >= 0 else 3.0 * hi, 1e-3, 1e3, -1.0, 1.0])))
         return float(np.float32(self.rng.uniform(lo, hi)))
+
+    def integer(self, lo, hi):
+        if self.wild and self.rng.random() < self.wild:
+            return int(self.rng.integers(lo - 2, hi + 3))
+        return int(self.rng.integers(lo, hi + 1))
 
     def bounded_leaf(self):
         lo = self.uniform(0.1, 0.5)
@@ -53,11 +63,13 @@ class TreeFuzzer:
             key = (v["name"], v["dim"]) if v["dim"] >= 0 else v["name"]
             if v["type"] == 0:
                 variables[key] = self.uniform(*FLOAT_RANGES[v["name"]])
+                if v["name"] == "Feature Scale" and variables[key] == 0.0:
+                    variables[key] = 1.0            # a zero scale is an infinite frequency: NaN positions everywhere below
             elif v["type"] == 1:
                 lo, hi = INT_RANGES[v["name"]]
-                variables[key] = int(self.rng.integers(lo, hi + 1))
+                variables[key] = self.integer(lo, hi) if v["name"] != "Seed Offset" else int(self.rng.integers(lo, hi + 1))
             else:
-                variables[key] = int(self.rng.integers(0, len(v["enums"])))
+                variables[key] = self.integer(0, len(v["enums"]) - 1)
         lookups = []
         for _ in meta["lookups"]:
             if node_id in WARP_FRACTAL_IDS:

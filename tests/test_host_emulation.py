@@ -7,6 +7,7 @@ nothing under fastnoise2_b200/ can evaluate noise on the CPU.
     python tests/test_host_emulation.py 2000 [seed base] [tree depth]   # offline fuzz with that many random trees per flavour
     FN2_FUZZ_GRIDS=far ...      grids far from the origin (big cell coordinates; Convert<int> overflow shows up in 4D)
     FN2_FUZZ_ENTRIES=1 ...      every tree also through the tileable and position-array entry kernels
+    FN2_FUZZ_WILD=0.25 ...      that share of the parameters leaves its sensible / valid range (NaN, inf, out-of-range enums)
     FN2_FUZZ_SETTERS=1 ...      random reflection-setter sequences (in- and out-of-range values) instead of encoded trees
     FASTNOISE2_B200_PACK=2 FASTNOISE2_B200_FILL=0 ...   the packed-FP32 form
 """
@@ -218,7 +219,7 @@ def test_random_setter_sequences_on_host_match_the_oracle(fn, ref, tmp_path):
 
 
 def fuzz(fn, ref_lib, count, seed, workdir, label, depth=3):
-    fuzzer = TreeFuzzer(seed)
+    fuzzer = TreeFuzzer(seed, wild=float(os.environ.get("FN2_FUZZ_WILD", "0")))
     failures = []
     for index in range(count):
         text = fuzzer.tree(depth=depth).encode()
@@ -288,8 +289,9 @@ if __name__ == "__main__":
     base = int(sys.argv[2]) if len(sys.argv) > 2 else 9000  # fuzzer seed: run several processes with different bases in parallel
     depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     if os.environ.get("FN2_FUZZ_SETTERS"):                      # random setter sequences instead of random encoded trees
-        product.set_math_mode(0)
-        for item in setter_fuzz(product, helpers.load_ref("strict_avx512"), total, base, tempfile.mkdtemp()):
+        generic = os.environ["FN2_FUZZ_SETTERS"] == "generic"
+        product.set_math_mode(2 if generic else 0)
+        for item in setter_fuzz(product, helpers.load_ref("strict_avx2" if generic else "strict_avx512"), total, base, tempfile.mkdtemp()):
             print(item)
         print("setter sequences done", flush=True)
         sys.exit(0)
