@@ -83,18 +83,19 @@ namespace fn2
         }
     }
 
-    // sorting network step of CellularDistance, entries 0..TOP [Cellular.inl:344-349]
-    template<int TOP, class F>
+    // sorting network step of CellularDistance, entries 0..TOP [Cellular.inl:344-349]. A candidate distance is never NaN while
+    // the position and the jitter / size jitter / Minkowski P inputs are finite, and FMNMX then equals minps / maxps; ORDERED
+    // (chosen by the lowering when one of those inputs is a node that may return NaN or inf) keeps the reference's operand
+    // order, in which a NaN candidate shifts the list: min( d, NaN ) = NaN, max( NaN, d[i-1] ) = d[i-1].
+    template<int TOP, bool ORDERED, class F>
     FN2_DI void distance_insert( F ( &distance )[4], F newDistance )
     {
-        typedef typename pack<F>::I I;
-        typedef typename pack<F>::B B;
 #pragma unroll
         for( int i = TOP; i > 0; i-- )
         {
-            distance[i] = max_( min_( distance[i], newDistance ), distance[i - 1] );
+            distance[i] = ORDERED ? max_x86( min_x86( distance[i], newDistance ), distance[i - 1] ) : max_( min_( distance[i], newDistance ), distance[i - 1] );
         }
-        distance[0] = min_( distance[0], newDistance );
+        distance[0] = ORDERED ? min_x86( distance[0], newDistance ) : min_( distance[0], newDistance );
     }
 
     // ================================================================== CellularValue [Cellular.inl:18-292]
@@ -236,7 +237,7 @@ namespace fn2
 
     // ================================================================== CellularDistance [Cellular.inl:295-529]
     // fills distance[0..TOP] with the ascending cell distances
-    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    template<int DF, bool SIZEJ, int TOP, bool ORDERED = false, class PF, class F>
     FN2_DI void cellular_distance2( i32 seed, F x, F y, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
         typedef typename pack<F>::I I;
@@ -262,7 +263,7 @@ namespace fn2
                 yd = fma_( yd, invMag, ycf - y );
                 F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd ) : 0.0f, xd, yd );
                 if( SIZEJ ) newDistance *= size_jitter2( hash, sizeJitter );
-                distance_insert<TOP>( distance, newDistance );
+                distance_insert<TOP, ORDERED>( distance, newDistance );
                 ycf += 1.0f;
                 yc = iadd( yc, kPY );
             }
@@ -271,7 +272,7 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    template<int DF, bool SIZEJ, int TOP, bool ORDERED = false, class PF, class F>
     FN2_DI void cellular_distance3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
         typedef typename pack<F>::I I;
@@ -304,7 +305,7 @@ namespace fn2
                     zd = fma_( zd, invMag, zcf - z );
                     F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd ) : 0.0f, xd, yd, zd );
                     if( SIZEJ ) newDistance *= size_jitter3( hash, sizeJitter );
-                    distance_insert<TOP>( distance, newDistance );
+                    distance_insert<TOP, ORDERED>( distance, newDistance );
                     zcf += 1.0f;
                     zc = iadd( zc, kPZ );
                 }
@@ -316,7 +317,7 @@ namespace fn2
         }
     }
 
-    template<int DF, bool SIZEJ, int TOP, class PF, class F>
+    template<int DF, bool SIZEJ, int TOP, bool ORDERED = false, class PF, class F>
     FN2_DI void cellular_distance4( i32 seed, F x, F y, F z, F w, F jitter, F sizeJitter, PF minkowskiP, F ( &distance )[4] )
     {
         typedef typename pack<F>::I I;
@@ -356,7 +357,7 @@ namespace fn2
                         wd = fma_( wd, invMag, wcf - w );
                         F newDistance = calc_distance<DF, false>( DF == 5 ? minkowskiP( xd, yd, zd, wd ) : 0.0f, xd, yd, zd, wd );
                         if( SIZEJ ) newDistance *= size_jitter4( hash, sizeJitter );
-                        distance_insert<TOP>( distance, newDistance );
+                        distance_insert<TOP, ORDERED>( distance, newDistance );
                         wcf += 1.0f;
                         wc = iadd( wc, kPW );
                     }

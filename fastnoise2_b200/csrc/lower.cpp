@@ -192,6 +192,15 @@ namespace
             }
         }
 
+        // A hybrid input that is finite at every finite position: a finite constant, or one of the bounded leaves with a finite
+        // frequency. The Cellular nodes keep FMNMX in their distance sorting network when all their inputs are like that.
+        static bool HybAlwaysFinite( const Generator* owner, int hybrid )
+        {
+            const Impl::NodeState::Hybrid& h = owner->State().hybrids[hybrid];
+            if( !h.node ) return std::isfinite( h.constant );
+            return FiniteOrNaN( h.node.get() ) && std::isfinite( h.node->State().f[F_Frequency] );
+        }
+
         // ScaleOutput [BasicGenerators.inl:27-30]: fma( (1/(max-min)) * rangeScale, value - min, rangeMin ), factor folded on the host in float
         static std::string Range( const Impl::NodeState& s, const std::string& value, float nativeMin, float nativeMax )
         {
@@ -368,7 +377,10 @@ namespace
                 if( ret < 0 || ret > 4 ) ret = 0;
                 int top = ( df == 0 || ret != 0 ) ? std::max( i0, i1 ) : i0;
                 b << "    F dist[4];\n";
-                b << "    fn2::cellular_distance" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top
+                // a NaN candidate distance (possible only through a non-finite jitter / size jitter / Minkowski P input) moves
+                // through the reference's min / max network in operand order: fn2::distance_insert<TOP, ORDERED>
+                const bool ordered = !HybAlwaysFinite( g, 1 ) || ( sizeJ && !HybAlwaysFinite( g, 2 ) ) || ( df == 5 && !HybAlwaysFinite( g, 0 ) );
+                b << "    fn2::cellular_distance" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ", " << top << ( ordered ? ", true" : "" )
                   << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, dist );\n";
                 if( df == 0 ) // GetReturn [Cellular.inl:533-537]; with index0 == index1 the entry is normalised twice, as there
                 {

@@ -135,9 +135,16 @@ namespace FS
         Register() = default;
         FS_FORCEINLINE Register( Vec raw, int ) : v( raw ) {}
 
-        // broadcast from any arithmetic scalar (sources pass int, unsigned, float and double constants)
+        // broadcast from any arithmetic scalar (sources pass int, unsigned, float and double constants); lane by lane like
+        // set1_ps, so that a -0.0f constant keeps its sign ( 0 + -0.0f would be +0.0f )
+        static FS_FORCEINLINE Vec Splat( T s )
+        {
+            Vec r;
+            for( int lane = 0; lane < (int)( sizeof( Vec ) / sizeof( T ) ); lane++ ) r[lane] = s;
+            return r;
+        }
         template<typename U, typename = std::enable_if_t<std::is_arithmetic<U>::value>>
-        FS_FORCEINLINE Register( U s ) : v( Vec{} + (T)s ) {}
+        FS_FORCEINLINE Register( U s ) : v( Splat( (T)s ) ) {}
 
         FS_FORCEINLINE vi_t bits() const { return (vi_t)v; }
         static FS_FORCEINLINE Register fromBits( vi_t b ) { return Register( (Vec)b, 0 ); }

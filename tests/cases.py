@@ -15,6 +15,9 @@ NON_FINITE_TREES = {
     "max_of_perlin_and_modulus_by_zero": "GwkICP0AAAAYlU2YvwQCLQL/AAAM",                       # Max( Perlin, Modulus( Perlin, 0 ) ): NaN second operand
     "ridged_over_divide_by_zero": "Dwgs/8U/CRgCGQkCAA0zxUEIuq5OvxCyXKG/FAO+2a0+BA==",         # FractalRidged( Divide( Abs( Checkerboard ), 0 ) ): inf source
     "maxsmooth_with_modulus_by_zero": "FgIdCRYCCiABAAAAAzC6P0ALSg/PPgwCLQIEABSeb78IheUQvxB5Puc+GKI0ML8Dzc3XvxvKYShAHA==",
+    "constant_minus_zero_under_rotate": "IQkjEDzgJ0AJAAAAAACAFA==",                        # a -0.0f constant keeps its sign (the oracle shim once lost it)
+    "cellular_distance_with_nan_jitter": "LgABAAAACSEJCwiaAwAAEK+Xhb8YAAAAgCABAAAAKAIAAAAwAwAAAAIGAND2HEIIMAAAABA8wpk+GNhfST8ECgYAAAAAAAgjAAAAEJIQhz4YEaYIPwQTlqvGPRQ=",
+    "cellular_distance_with_nan_size_jitter": "FwkWAgYIdvz//xgAAMBADAILAGONZUEYerruPiAFAAAAKAQAAAACCQBVin1BCCYAAAAQl726Phh2yiU/BBIJAAAAAAAILAAAABCkNKg+GEOjQz8U",
     "nested_blends_with_signed_zeros": "KAACAAAAER8CFQkHAJzo+0EIFAAAABCtlkI+GNOPob8EA5a61j4EC8IoTz8EAAQCLQIKGODqZ78gAQAAACgAAAAAAgkAyBgQQQgSAAAAEO2s1z4Y1GczPwQTpzEgPgQKKgkBACf8//8I3hmEPxAYotE+BAPCTD0+DAtF6VG9EzV7Kz4E",
 }
 
