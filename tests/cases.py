@@ -18,6 +18,7 @@ NON_FINITE_TREES = {
     "constant_minus_zero_under_rotate": "IQkjEDzgJ0AJAAAAAACAFA==",                        # a -0.0f constant keeps its sign (the oracle shim once lost it)
     "cellular_distance_with_nan_jitter": "LgABAAAACSEJCwiaAwAAEK+Xhb8YAAAAgCABAAAAKAIAAAAwAwAAAAIGAND2HEIIMAAAABA8wpk+GNhfST8ECgYAAAAAAAgjAAAAEJIQhz4YEaYIPwQTlqvGPRQ=",
     "cellular_distance_with_nan_size_jitter": "FwkWAgYIdvz//xgAAMBADAILAGONZUEYerruPiAFAAAAKAQAAAACCQBVin1BCCYAAAAQl726Phh2yiU/BBIJAAAAAAAILAAAABCkNKg+GEOjQz8U",
+    "max_axis_distance_to_a_nan_point": "KAACAAAAEQIAt63SwQhlJ4m/BAUABAAAAAItAgcAORAfQgjw/f//EAAAwEAYjWjvvwwT4PORQBoFAAQAAAACCwBvEoM6CAQBAAAQ9e/ovxjzQp8/IAIAAAAoAgAAADAAAAAAOP7///8D516dPwtBnTo/E28SgzoECgkAICnpQQgQAwAAEC5w278EEgUAAgAAABsx6bm/IwAAgD8EG9KzhD8iCAAAAACACCUAAAAQ2q3FPhjMRTc/FAouAAAAAAAJLgkKAKwRH0EQ/3e2vxhvEoM6KAIAAAADEtIEQAvCY3w/EyW3iz4c",
     "nested_blends_with_signed_zeros": "KAACAAAAER8CFQkHAJzo+0EIFAAAABCtlkI+GNOPob8EA5a61j4EC8IoTz8EAAQCLQIKGODqZ78gAQAAACgAAAAAAgkAyBgQQQgSAAAAEO2s1z4Y1GczPwQTpzEgPgQKKgkBACf8//8I3hmEPxAYotE+BAPCTD0+DAtF6VG9EzV7Kz4E",
 }
 
