@@ -68,6 +68,7 @@ PROTOTYPES = {
     "fnb200GetMathMode": (I, []),
     "fnb200Prepare": (I, [P, I]),
     "fnb200GetKernelSource": (ctypes.c_long, [P, I, P, ctypes.c_long]),
+    "fnb200GetKernelParams": (ctypes.c_long, [P, I, P, ctypes.c_long]),
     "fnb200SelfTestInvSqrt": (LL, [F, F]),
     "fnb200SelfTestLeaf": (I, [I, I, I, I, F, P]),
     "fnb200MinMaxReset": (I, [P, P]),
@@ -81,6 +82,11 @@ PROTOTYPES = {
     "fnb200MeasureAluPeak": (ctypes.c_double, [I, I]),
     "fnb200CanonicalEncodedNodeTree": (ctypes.c_long, [S, P, ctypes.c_long]),
     "fnb200LaunchCount": (ctypes.c_ulonglong, []),
+    "fnb200CommGetUniqueId": (I, [P]),
+    "fnb200CommInitRank": (P, [I, I, P]),
+    "fnb200CommDestroy": (I, [P]),
+    "fnb200CommAllReduceMinMax": (I, [P, P, P]),
+    "fnb200CommGatherSlabs": (I, [P, P, P, P, P]),
 }
 
 

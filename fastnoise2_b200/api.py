@@ -10,17 +10,7 @@ lib = _lib.load()
 KIND_GRID2D, KIND_GRID3D, KIND_GRID4D, KIND_TILEABLE2D = 2, 3, 4, 5
 KIND_POS2D, KIND_POS3D, KIND_POS4D = 12, 13, 14
 
-# Encoded trees of the five BASELINE.json configs (each decodes with the reference's own decoder)
-TREES = {
-    "fbm_simplex_readme": "DQkGDA==",          # FastNoise.h:53 example: FractalFBm( Simplex )
-    "c1_simplex": "BgQ=",                      # config 1: Simplex, 3D grid 256^3
-    "c2_fbm5_perlin": "DQAFAAAACQgM",          # config 2: FractalFBm( 5 octaves, Perlin ), 2D grid 16384^2 / tileable 4096^2
-    "c3a_cellular_distance": "CwQ=",           # config 3: CellularDistance, 3D grid 512^3
-    "c3b_cellular_lookup_white": "DAkBDA==",   # config 3: CellularLookup( White ): output equal <=> same cell, bit for bit
-    "c3c_cellular_lookup_gradient": "DAkEAArXIzwI93VgPBCad5w8DA==",
-    "c4_terrain": "EwkSAAAASEMJKgAAAEBBCSkAAQAAAAkdCQ0ABQAAAAkGAAAAFkMMAg8ABAAAAAkIAAAAtEIIBwAAAAwLzcxMPgQLAAAAQAQDAACAPgQDAADwQQw=",
-    "c5_supersimplex": "BwQ=",                 # config 5: SuperSimplex, 4D position array
-}
+from .trees import TREES  # noqa: E402,F401  (pure data: importable without the native library)
 
 
 def device_available():
@@ -84,6 +74,15 @@ class Generator:
         buf = ctypes.create_string_buffer(n + 1)
         lib.fnb200GetKernelSource(self.handle, kind, buf, n + 1)
         return buf.value.decode()
+
+    def kernel_params(self, kind):
+        """Current values of the kernel's float-parameter argument (fnb200GetKernelParams), as a float32 array."""
+        n = lib.fnb200GetKernelParams(self.handle, kind, None, 0)
+        if n < 0:
+            raise RuntimeError(last_error())
+        buf = np.zeros(max(n, 1), np.float32)
+        lib.fnb200GetKernelParams(self.handle, kind, buf.ctypes.data, n)
+        return buf
 
     def prepare(self, kind):
         rc = lib.fnb200Prepare(self.handle, kind)

@@ -1,11 +1,13 @@
 // fastnoise2_b200 -- the B200 backend behind FastNoise::Generator::Gen*.
 //
 // What the reference does with FastSIMD::NewDispatchClass + virtual Gen() calls is done here in three
-// steps: (1) lower the tree to CUDA source (lower.cpp), (2) compile it for sm_100a with NVRTC -- cached in
-// memory and on disk by source hash, so a given tree shape/parameter set is compiled once per machine --
-// and load the cubin as a CUDA library, (3) launch the entry kernel over the requested points.
+// steps: (1) lower the tree to CUDA source (lower.cpp) -- float node parameters become kernel arguments, so the text
+// depends on the SHAPE of the tree only, (2) compile it for sm_100a with NVRTC -- cached in memory and on disk by
+// source hash, so a given tree shape is compiled once per machine -- and load the cubin as a CUDA library,
+// (3) launch the persistent entry kernel over the requested points with the tree's current parameter values.
 // Host output / position pointers go through a double-buffered device staging pipeline so copies overlap
-// the kernels; device pointers are used in place. There is no CPU evaluation path: if CUDA or NVRTC is
+// the kernels -- split over every visible GPU for large calls, each GPU draining its rows over its own PCIe link --
+// and device pointers are used in place. There is no CPU evaluation path: if CUDA or NVRTC is
 // unavailable every Gen* call fails (empty OutputMinMax, fnb200LastError() says why).
 #include "backend.h"
 
@@ -17,14 +19,18 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -70,6 +76,7 @@ namespace
     {
         cudaLibrary_t library = nullptr;
         cudaKernel_t kernel = nullptr;
+        int residentBlocks = 0; // blocks of kBlock threads the whole device keeps resident: the persistent launch size
     };
 
     std::string CacheDir()
@@ -159,13 +166,23 @@ namespace
         return cubin;
     }
 
+    std::uint64_t LibraryTextHash()
+    {
+        static const std::uint64_t h = []
+        {
+            std::uint64_t v = 1469598103934665603ull;
+            for( int i = 0; i < kEmbeddedDeviceSourceCount; i++ ) v = Fnv64( kEmbeddedDeviceSourceText[i], v );
+            return v;
+        }();
+        return h;
+    }
+
     std::vector<char> CubinFor( const std::string& source, int mathMode, std::string& error )
     {
-        std::string key = source;
-        for( const std::string& o : CompileOptions( mathMode ) ) key += "\n//" + o;
-        for( int i = 0; i < kEmbeddedDeviceSourceCount; i++ ) key += kEmbeddedDeviceSourceText[i];
+        std::uint64_t key = Fnv64( source, LibraryTextHash() );
+        for( const std::string& o : CompileOptions( mathMode ) ) key = Fnv64( "\n//" + o, key );
         char name[64];
-        std::snprintf( name, sizeof( name ), "/%016llx.cubin", (unsigned long long)Fnv64( key ) );
+        std::snprintf( name, sizeof( name ), "/%016llx.cubin", (unsigned long long)key );
         const std::string path = CacheDir() + name;
 
         {
@@ -195,11 +212,11 @@ namespace
     std::mutex gModuleMutex;
     std::map<std::pair<std::uint64_t, int>, Module> gModules; // (source hash, device) -> loaded kernel
 
-    const Module* LoadModule( const std::string& source, int mathMode, int device, std::string& error )
+    // the current device must be `device`
+    const Module* LoadModule( const std::string& source, std::uint64_t sourceHash, int mathMode, int device, std::string& error )
     {
-        const std::uint64_t hash = Fnv64( source, Fnv64( "math mode " + std::to_string( mathMode ) ) );
         std::lock_guard<std::mutex> lock( gModuleMutex );
-        auto it = gModules.find( { hash, device } );
+        auto it = gModules.find( { sourceHash, device } );
         if( it != gModules.end() ) return &it->second;
 
         std::vector<char> cubin = CubinFor( source, mathMode, error );
@@ -221,32 +238,130 @@ namespace
             cudaLibraryUnload( m.library );
             return nullptr;
         }
-        return &gModules.emplace( std::make_pair( hash, device ), m ).first->second;
+        int perSm = 0, sms = 0;
+        if( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, (const void*)m.kernel, kBlock, 0 ) != cudaSuccess || perSm < 1 )
+        {
+            cudaGetLastError();
+            perSm = 2;
+        }
+        if( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, device ) != cudaSuccess || sms < 1 )
+        {
+            cudaGetLastError();
+            sms = 148;
+        }
+        m.residentBlocks = perSm * sms;
+        return &gModules.emplace( std::make_pair( sourceHash, device ), m ).first->second;
     }
 
-    // ------------------------------------------------------------------ per-thread CUDA context
-    struct ThreadContext
+    // ------------------------------------------------------------------ host-side copy workers (pageable destinations)
+    // cudaMemcpyAsync into pageable memory is staged by the driver through one small pinned buffer and runs at a fraction of the
+    // link rate. Pageable destinations therefore go device -> pinned bounce buffer (DMA at link rate) -> destination, the second
+    // hop done by a few worker threads while the next chunk is computed and transferred.
+    class CopyPool
+    {
+    public:
+        struct Ticket
+        {
+            std::mutex mutex;
+            std::condition_variable done;
+            int pending = 0;
+            void Wait()
+            {
+                std::unique_lock<std::mutex> lock( mutex );
+                done.wait( lock, [this] { return pending == 0; } );
+            }
+        };
+
+        static CopyPool& Get()
+        {
+            static CopyPool* pool = new CopyPool; // never destroyed: worker threads may outlive static destruction
+            return *pool;
+        }
+
+        int Threads() const { return (int)mWorkers.size(); }
+
+        // after `ready` (an event recorded behind the DMA into `src`) has completed, copy bytes src -> dst on the workers
+        void Submit( cudaEvent_t ready, const char* src, char* dst, std::size_t bytes, Ticket& ticket )
+        {
+            const int parts = (int)std::max<std::size_t>( 1, std::min<std::size_t>( mWorkers.size(), bytes / ( 1u << 20 ) ) );
+            {
+                std::lock_guard<std::mutex> lock( ticket.mutex );
+                ticket.pending += parts;
+            }
+            const std::size_t slice = ( ( bytes / parts ) + 63 ) & ~std::size_t( 63 );
+            std::lock_guard<std::mutex> lock( mMutex );
+            for( int p = 0; p < parts; p++ )
+            {
+                const std::size_t begin = std::min( bytes, slice * p ), end = p == parts - 1 ? bytes : std::min( bytes, slice * ( p + 1 ) );
+                mJobs.push_back( [=, &ticket]
+                {
+                    cudaEventSynchronize( ready );
+                    if( end > begin ) std::memcpy( dst + begin, src + begin, end - begin );
+                    std::lock_guard<std::mutex> l( ticket.mutex );
+                    if( --ticket.pending == 0 ) ticket.done.notify_all();
+                } );
+            }
+            mWake.notify_all();
+        }
+
+    private:
+        CopyPool()
+        {
+            int n = EnvInt( "FASTNOISE2_B200_COPY_THREADS", 0 );
+            if( n <= 0 ) n = (int)std::min<unsigned>( 8, std::max<unsigned>( 2, std::thread::hardware_concurrency() / 2 ) );
+            for( int i = 0; i < n; i++ )
+            {
+                mWorkers.emplace_back( [this]
+                {
+                    for( ;; )
+                    {
+                        std::function<void()> job;
+                        {
+                            std::unique_lock<std::mutex> lock( mMutex );
+                            mWake.wait( lock, [this] { return !mJobs.empty(); } );
+                            job = std::move( mJobs.front() );
+                            mJobs.pop_front();
+                        }
+                        job();
+                    }
+                } );
+                mWorkers.back().detach();
+            }
+        }
+
+        std::mutex mMutex;
+        std::condition_variable mWake;
+        std::deque<std::function<void()>> mJobs;
+        std::vector<std::thread> mWorkers;
+    };
+
+    // ------------------------------------------------------------------ per-thread, per-device CUDA resources
+    struct DeviceContext
     {
         int device = -1;
         cudaStream_t compute = nullptr, copyOut = nullptr, copyIn = nullptr;
-        cudaEvent_t computed[2] = {}, drained[2] = {}, uploaded[2] = {};
+        cudaEvent_t computed[2] = {}, drained[2] = {}, uploaded[2] = {}, callerDone = nullptr;
         float* outBuf[2] = {};
         std::size_t outCap = 0; // floats per buffer
         float* inBuf[2][4] = {};
         std::size_t inCap = 0;
+        int inDims = 0;
+        float* bounce[2] = {}; // pinned host, pageable destinations only
+        std::size_t bounceCap = 0;
+        CopyPool::Ticket bounceBusy[2];
         unsigned* minMax = nullptr;     // device accumulator
         unsigned* minMaxHost = nullptr; // pinned
 
-        bool Ensure()
+        // the current device must be `device`
+        bool Ensure( int dev )
         {
-            int current = 0;
-            if( !Check( cudaGetDevice( &current ), "cudaGetDevice" ) ) return false;
-            if( device == current && compute ) return true;
+            if( device == dev && compute ) return true;
             Release();
-            device = current;
+            device = dev;
             bool ok = Check( cudaStreamCreateWithFlags( &compute, cudaStreamNonBlocking ), "cudaStreamCreate" ) &&
                       Check( cudaStreamCreateWithFlags( &copyOut, cudaStreamNonBlocking ), "cudaStreamCreate" ) &&
-                      Check( cudaStreamCreateWithFlags( &copyIn, cudaStreamNonBlocking ), "cudaStreamCreate" );
+                      Check( cudaStreamCreateWithFlags( &copyIn, cudaStreamNonBlocking ), "cudaStreamCreate" ) &&
+                      Check( cudaEventCreateWithFlags( &callerDone, cudaEventDisableTiming ), "cudaEventCreate" );
             for( int i = 0; ok && i < 2; i++ )
             {
                 ok = Check( cudaEventCreateWithFlags( &computed[i], cudaEventDisableTiming ), "cudaEventCreate" ) &&
@@ -271,24 +386,42 @@ namespace
 
         bool EnsureIn( std::size_t floats, int dims )
         {
-            if( floats <= inCap ) return true;
+            if( floats <= inCap && dims <= inDims ) return true;
+            floats = std::max( floats, inCap );
+            dims = std::max( dims, inDims );
             for( auto& pair : inBuf ) for( float*& b : pair ) { if( b ) cudaFree( b ); b = nullptr; }
             inCap = 0;
-            for( auto& pair : inBuf ) for( int d = 0; d < 4; d++ )
+            inDims = 0;
+            for( auto& pair : inBuf ) for( int d = 0; d < dims; d++ )
             {
-                (void)dims;
                 if( !Check( cudaMalloc( &pair[d], floats * sizeof( float ) ), "cudaMalloc(staging in)" ) ) return false;
             }
             inCap = floats;
+            inDims = dims;
+            return true;
+        }
+
+        bool EnsureBounce( std::size_t floats )
+        {
+            if( floats <= bounceCap ) return true;
+            for( float*& b : bounce ) { if( b ) cudaFreeHost( b ); b = nullptr; }
+            bounceCap = 0;
+            for( float*& b : bounce ) if( !Check( cudaMallocHost( &b, floats * sizeof( float ) ), "cudaMallocHost(bounce)" ) ) return false;
+            bounceCap = floats;
             return true;
         }
 
         void Release()
         {
             if( device < 0 ) return;
+            int previous = -1;
+            if( cudaGetDevice( &previous ) == cudaSuccess && previous != device ) cudaSetDevice( device );
+            for( CopyPool::Ticket& t : bounceBusy ) t.Wait();
             for( float*& b : outBuf ) { if( b ) cudaFree( b ); b = nullptr; }
             for( auto& pair : inBuf ) for( float*& b : pair ) { if( b ) cudaFree( b ); b = nullptr; }
-            outCap = inCap = 0;
+            for( float*& b : bounce ) { if( b ) cudaFreeHost( b ); b = nullptr; }
+            outCap = inCap = bounceCap = 0;
+            inDims = 0;
             if( minMax ) cudaFree( minMax );
             if( minMaxHost ) cudaFreeHost( minMaxHost );
             minMax = minMaxHost = nullptr;
@@ -299,28 +432,54 @@ namespace
                 if( uploaded[i] ) cudaEventDestroy( uploaded[i] );
                 computed[i] = drained[i] = uploaded[i] = nullptr;
             }
+            if( callerDone ) cudaEventDestroy( callerDone );
+            callerDone = nullptr;
             if( compute ) cudaStreamDestroy( compute );
             if( copyOut ) cudaStreamDestroy( copyOut );
             if( copyIn ) cudaStreamDestroy( copyIn );
             compute = copyOut = copyIn = nullptr;
             device = -1;
+            if( previous >= 0 ) cudaSetDevice( previous );
             cudaGetLastError();
         }
-
-        ~ThreadContext() { /* leaked on purpose at thread exit: the CUDA runtime may already be torn down */ }
     };
 
-    thread_local ThreadContext tContext;
+    // One DeviceContext per device this thread has used. Released when the thread exits: a consumer that spawns short-lived worker
+    // threads must not leak staging memory per thread. At process exit the CUDA runtime may already be unloading -- every call in
+    // Release() then fails with cudaErrorCudartUnloading, which is ignored.
+    struct ThreadContexts
+    {
+        std::vector<std::unique_ptr<DeviceContext>> perDevice;
 
-    bool IsDevicePointer( const void* p )
+        // makes `device` current
+        DeviceContext* Get( int device )
+        {
+            if( !Check( cudaSetDevice( device ), "cudaSetDevice" ) ) return nullptr;
+            if( (std::size_t)device >= perDevice.size() ) perDevice.resize( device + 1 );
+            if( !perDevice[device] ) perDevice[device].reset( new DeviceContext );
+            return perDevice[device]->Ensure( device ) ? perDevice[device].get() : nullptr;
+        }
+
+        ~ThreadContexts()
+        {
+            for( auto& c : perDevice ) if( c ) c->Release();
+        }
+    };
+
+    thread_local ThreadContexts tContexts;
+
+    enum class Memory { Device, Pinned, Pageable };
+
+    Memory Classify( const void* p )
     {
         cudaPointerAttributes attr {};
         if( cudaPointerGetAttributes( &attr, p ) != cudaSuccess )
         {
             cudaGetLastError();
-            return false;
+            return Memory::Pageable;
         }
-        return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+        if( attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged ) return Memory::Device;
+        return attr.type == cudaMemoryTypeHost ? Memory::Pinned : Memory::Pageable;
     }
 
     FastDivHost MakeFastDiv( unsigned d )
@@ -363,6 +522,11 @@ namespace FastNoise
             return mm;
         }
 
+        static bool ParamMode()
+        {
+            return EnvInt( "FASTNOISE2_B200_LITERALS", 0 ) == 0;
+        }
+
         // --------------------------------------------------------------- per-root compiled programs
         struct CompiledTree
         {
@@ -370,8 +534,11 @@ namespace FastNoise
             {
                 std::uint64_t stamp = 0;
                 std::string source;
+                std::uint64_t sourceHash = 0;
+                std::vector<float> params;
                 std::string error;
                 int mathMode = 0;
+                bool paramMode = false;
             };
             std::mutex mutex;
             std::map<int, Variant> variants; // key = kind * 16 + ppt
@@ -389,45 +556,69 @@ namespace FastNoise
 
         void ReleaseCompiled( CompiledTree* compiled ) { delete compiled; }
 
-        // source text for (root, kind, ppt), re-lowered only when some node parameter changed since last time
-        static bool SourceFor( const Generator* root, int kind, int ppt, std::string& source, int& mathMode )
+        // What one launch needs of (root, kind, ppt): the program text (re-lowered only when some node parameter changed since
+        // last time; a float edit gives the same text back, so the loaded kernel is found again by its hash) and the values
+        // of the kernel's TreeParams argument.
+        struct Program
+        {
+            std::string source;
+            std::uint64_t sourceHash = 0;
+            std::vector<float> params;
+            int mathMode = 0;
+        };
+
+        static bool ProgramFor( const Generator* root, int kind, int ppt, Program& program, bool wantSource )
         {
             CompiledTree* tree = CompiledTree::Of( root );
             std::lock_guard<std::mutex> lock( tree->mutex );
             CompiledTree::Variant& v = tree->variants[kind * 16 + ppt];
             const std::uint64_t stamp = TreeStamp();
             const int mode = MathMode();
-            if( v.stamp != stamp || v.mathMode != mode || ( v.source.empty() && v.error.empty() ) )
+            const bool paramMode = ParamMode();
+            if( v.stamp != stamp || v.mathMode != mode || v.paramMode != paramMode || ( v.source.empty() && v.error.empty() ) )
             {
-                LoweredProgram lowered = LowerTree( root, kind, ppt, mode );
-                v.source = std::move( lowered.source );
+                LoweredProgram lowered = LowerTree( root, kind, ppt, mode, paramMode );
+                if( lowered.source != v.source || v.mathMode != mode )
+                {
+                    v.source = std::move( lowered.source );
+                    v.sourceHash = Fnv64( v.source, Fnv64( "math mode " + std::to_string( mode ) ) );
+                }
+                v.params = std::move( lowered.params );
                 v.error = std::move( lowered.error );
                 v.stamp = stamp;
                 v.mathMode = mode;
+                v.paramMode = paramMode;
             }
             if( !v.error.empty() )
             {
                 SetLastError( "cannot lower node tree: " + v.error );
                 return false;
             }
-            source = v.source;
-            mathMode = v.mathMode;
+            if( wantSource ) program.source = v.source;
+            program.sourceHash = v.sourceHash;
+            program.params = v.params;
+            program.mathMode = v.mathMode;
             return true;
         }
 
         std::string KernelSource( const Generator* root, int kind, int ppt )
         {
-            std::string source;
-            int mode;
-            return SourceFor( root, kind, ppt, source, mode ) ? source : std::string();
+            Program program;
+            return ProgramFor( root, kind, ppt, program, true ) ? program.source : std::string();
+        }
+
+        std::vector<float> KernelParams( const Generator* root, int kind, int ppt )
+        {
+            Program program;
+            return ProgramFor( root, kind, ppt, program, false ) ? program.params : std::vector<float>();
         }
 
         int PrepareOffline( const Generator* root, int kind, int ppt )
         {
-            std::string source, error;
-            int mode;
-            if( !SourceFor( root, kind, ppt, source, mode ) ) return -4;
-            if( CubinFor( source, mode, error ).empty() )
+            Program program;
+            std::string error;
+            if( !ProgramFor( root, kind, ppt, program, true ) ) return -4;
+            if( CubinFor( program.source, program.mathMode, error ).empty() )
             {
                 SetLastError( error );
                 return -3;
@@ -435,25 +626,32 @@ namespace FastNoise
             return 0;
         }
 
-        // 0 or FNB200_E* (-2 CUDA, -3 compile, -4 unsupported tree)
-        static int ModuleFor( const Generator* root, int kind, int ppt, const Module*& module )
+        // 0 or FNB200_E* (-2 CUDA, -3 compile, -4 unsupported tree); the current device is the one launched on
+        static int ModuleFor( const Generator* root, int kind, int ppt, const Module*& module, Program& program )
         {
-            std::string source, error;
-            int mode;
             module = nullptr;
-            if( !SourceFor( root, kind, ppt, source, mode ) ) return -4;
+            if( !ProgramFor( root, kind, ppt, program, false ) ) return -4;
             int device = 0;
             if( !Check( cudaGetDevice( &device ), "cudaGetDevice" ) ) return -2;
-            module = LoadModule( source, mode, device, error );
+            {
+                std::lock_guard<std::mutex> lock( gModuleMutex );
+                auto it = gModules.find( { program.sourceHash, device } );
+                if( it != gModules.end() ) module = &it->second;
+            }
+            if( module ) return 0;
+            std::string error;
+            if( !ProgramFor( root, kind, ppt, program, true ) ) return -4;
+            module = LoadModule( program.source, program.sourceHash, program.mathMode, device, error );
             if( module ) return 0;
             SetLastError( error );
             return error.compare( 0, 5, "nvrtc" ) == 0 || error.compare( 0, 5, "NVRTC" ) == 0 ? -3 : -2;
         }
 
+        // Points per thread: 4 (one 16-byte store per thread, neighbouring points share what does not depend on x) needs rows that
+        // are a multiple of 4 wide and a call large enough to fill the GPU that way; everything else runs one point per thread.
         static int MaxPointsPerThread()
         {
-            int p = EnvInt( "FASTNOISE2_B200_PPT", 4 );
-            return p >= 8 ? 8 : ( p >= 4 ? 4 : ( p >= 2 ? 2 : 1 ) );
+            return EnvInt( "FASTNOISE2_B200_PPT", 4 ) >= 4 ? 4 : 1;
         }
 
         // Threads the current device keeps resident (SM count x 2048): below that a call cannot fill the GPU, so it is worth
@@ -473,15 +671,17 @@ namespace FastNoise
         static int PointsPerThreadFor( unsigned long long points, int ppt )
         {
             if( EnvInt( "FASTNOISE2_B200_FILL", 1 ) == 0 ) return ppt; // tests: keep the large-call code path for small calls
-            while( ppt > 1 && points / (unsigned)ppt < ResidentThreads() ) ppt >>= 1;
-            return ppt;
+            return ppt > 1 && points / (unsigned)ppt < ResidentThreads() ? 1 : ppt;
         }
 
         // --------------------------------------------------------------- launches (device pointers)
-        static bool Launch( const Module* m, unsigned long long threads, void** args, cudaStream_t stream )
+        static bool Launch( const Module* m, unsigned long long groups, void** args, cudaStream_t stream )
         {
-            const unsigned long long blocks = ( threads + kBlock - 1 ) / kBlock;
+            unsigned long long blocks = ( groups + kBlock - 1 ) / kBlock;
             if( blocks == 0 ) return true;
+            // persistent: no more blocks than the device keeps resident; the kernel's grid-stride loop covers the rest
+            const unsigned long long resident = (unsigned long long)std::max( 1, m->residentBlocks ) * (unsigned)std::max( 1, EnvInt( "FASTNOISE2_B200_WAVES", 1 ) );
+            if( EnvInt( "FASTNOISE2_B200_PERSISTENT", 1 ) != 0 ) blocks = std::min( blocks, resident );
             if( blocks > 0x7fffffffull )
             {
                 SetLastError( "launch too large" );
@@ -497,19 +697,21 @@ namespace FastNoise
             const unsigned nx = (unsigned)call.count[0];
             const unsigned long long points = rowCount * nx;
             if( points == 0 ) return 0;
-            if( points >= 0x80000000ull || rowBegin + rowCount > 0xffffffffull )
+            // the kernel's index arithmetic (fn2::fast_div) is exact below 2^31, for points and for rows of the full grid alike
+            if( points >= 0x80000000ull || rowBegin + rowCount >= 0x80000000ull )
             {
-                SetLastError( "a single launch is limited to 2^31 - 1 points" );
+                SetLastError( "a single launch is limited to 2^31 - 1 points, and a grid to 2^31 - 1 rows" );
                 return -1;
             }
-            int ppt = MaxPointsPerThread();
-            while( ppt > 1 && nx % (unsigned)ppt != 0 ) ppt >>= 1;
-            ppt = PointsPerThreadFor( points, ppt );
+            const int ppt = nx % 4u == 0 ? PointsPerThreadFor( points, MaxPointsPerThread() ) : 1;
 
             const Module* m = nullptr;
-            if( int rc = ModuleFor( root, call.kind, ppt, m ) ) return rc;
+            Program program;
+            if( int rc = ModuleFor( root, call.kind, ppt, m, program ) ) return rc;
+            if( program.params.empty() ) program.params.push_back( 0.0f );
 
             int seed = call.seed;
+            const unsigned long long groups = points / (unsigned)ppt;
             if( call.kind == kTileable2D )
             {
                 TileArgsHost a {};
@@ -526,9 +728,10 @@ namespace FastNoise
                 a.rowBegin = (unsigned)rowBegin;
                 a.total = (unsigned)points;
                 a.vecStore = ( (std::uintptr_t)deviceOut % 16 ) == 0;
+                a.groups = (unsigned)groups;
                 a.divX = MakeFastDiv( nx );
-                void* args[] = { &deviceOut, &a, &deviceMinMax, &seed };
-                return Launch( m, ( points + ppt - 1 ) / ppt, args, stream ) ? 0 : -2;
+                void* args[] = { &deviceOut, &a, &deviceMinMax, &seed, program.params.data() };
+                return Launch( m, groups, args, stream ) ? 0 : -2;
             }
 
             GridArgsHost a {};
@@ -541,20 +744,23 @@ namespace FastNoise
             a.rowBegin = (unsigned)rowBegin;
             a.total = (unsigned)points;
             a.vecStore = ( (std::uintptr_t)deviceOut % 16 ) == 0;
+            a.groups = (unsigned)groups;
             a.divX = MakeFastDiv( nx );
             a.divY = MakeFastDiv( (unsigned)call.count[1] );
             a.divZ = MakeFastDiv( (unsigned)call.count[2] );
-            void* args[] = { &deviceOut, &a, &deviceMinMax, &seed };
-            return Launch( m, ( points + ppt - 1 ) / ppt, args, stream ) ? 0 : -2;
+            void* args[] = { &deviceOut, &a, &deviceMinMax, &seed, program.params.data() };
+            return Launch( m, groups, args, stream ) ? 0 : -2;
         }
 
         int LaunchPositions( const Generator* root, int dims, float* deviceOut, unsigned long long count, const float* const pos[4],
                              const float offset[4], int seed, unsigned* deviceMinMax, cudaStream_t stream )
         {
             if( count == 0 ) return 0;
-            const int ppt = PointsPerThreadFor( count, MaxPointsPerThread() > 4 ? 4 : MaxPointsPerThread() );
+            const int ppt = PointsPerThreadFor( count, MaxPointsPerThread() );
             const Module* m = nullptr;
-            if( int rc = ModuleFor( root, 10 + dims, ppt, m ) ) return rc;
+            Program program;
+            if( int rc = ModuleFor( root, 10 + dims, ppt, m, program ) ) return rc;
+            if( program.params.empty() ) program.params.push_back( 0.0f );
 
             PosArgsHost a {};
             bool aligned = ( (std::uintptr_t)deviceOut % 16 ) == 0;
@@ -565,25 +771,83 @@ namespace FastNoise
                 if( d < dims ) aligned = aligned && ( (std::uintptr_t)pos[d] % 16 ) == 0;
             }
             a.count = count;
+            a.groups = ( count + ppt - 1 ) / ppt;
             a.vecIO = aligned;
-            void* args[] = { &deviceOut, &a, &deviceMinMax, &seed };
-            return Launch( m, ( count + ppt - 1 ) / ppt, args, stream ) ? 0 : -2;
+            void* args[] = { &deviceOut, &a, &deviceMinMax, &seed, program.params.data() };
+            return Launch( m, a.groups, args, stream ) ? 0 : -2;
+        }
+
+        int PrepareAll( const Generator* root, int kind )
+        {
+            // every variant the launchers above can choose
+            for( int ppt : { 4, 1 } )
+            {
+                if( ppt > MaxPointsPerThread() ) continue;
+                if( int rc = PrepareOffline( root, kind, ppt ) ) return rc;
+            }
+            return 0;
         }
 
         // --------------------------------------------------------------- reference-shaped calls (host or device pointers)
         static std::size_t ChunkFloats()
         {
-            // staging buffer size per pipeline slot; two slots are allocated per calling thread
+            // staging buffer size per pipeline slot; two slots are allocated per calling thread and device
             return (std::size_t)EnvInt( "FASTNOISE2_B200_STAGING_MB", 64 ) * 1024 * 1024 / sizeof( float );
         }
 
-        static bool ReadMinMax( ThreadContext& ctx, OutputMinMax& mm )
+        // A reference-shaped call has no stream argument: work the caller queued earlier on the legacy default stream (and, through
+        // it, on every blocking stream) is ordered before this call's kernels; producers on NON-blocking streams must be
+        // synchronised by the caller.
+        static bool OrderAfterCaller( DeviceContext& ctx )
+        {
+            return Check( cudaEventRecord( ctx.callerDone, cudaStreamLegacy ), "cudaEventRecord(legacy stream)" ) &&
+                   Check( cudaStreamWaitEvent( ctx.compute, ctx.callerDone, 0 ), "cudaStreamWaitEvent" );
+        }
+
+        static bool ReadMinMax( DeviceContext& ctx, unsigned keys[2] )
         {
             if( !Check( cudaMemcpyAsync( ctx.minMaxHost, ctx.minMax, 2 * sizeof( unsigned ), cudaMemcpyDeviceToHost, ctx.compute ), "cudaMemcpyAsync(minmax)" ) ) return false;
             if( !Check( cudaStreamSynchronize( ctx.compute ), "cudaStreamSynchronize" ) ) return false;
-            mm = DecodeMinMax( ctx.minMaxHost );
+            keys[0] = std::max( keys[0], ctx.minMaxHost[0] );
+            keys[1] = std::max( keys[1], ctx.minMaxHost[1] );
             return true;
         }
+
+        // Devices a host-destination call of `points` points is spread over: the current one, plus every other visible sm_100 GPU
+        // when the call is large enough for the extra PCIe links to matter (FASTNOISE2_B200_FANOUT=0 disables, =N caps).
+        static std::vector<int> FanoutDevices( int current, unsigned long long points )
+        {
+            std::vector<int> devices { current };
+            const int cap = EnvInt( "FASTNOISE2_B200_FANOUT", 1024 );
+            const unsigned long long minPoints = (unsigned long long)EnvInt( "FASTNOISE2_B200_FANOUT_MIN_MPOINTS", 32 ) << 20;
+            int count = 0;
+            if( cap <= 1 || points < minPoints || cudaGetDeviceCount( &count ) != cudaSuccess ) return devices;
+            for( int d = 0; d < count && (int)devices.size() < cap; d++ )
+            {
+                int major = 0;
+                if( d != current && cudaDeviceGetAttribute( &major, cudaDevAttrComputeCapabilityMajor, d ) == cudaSuccess && major == 10 ) devices.push_back( d );
+            }
+            cudaGetLastError();
+            return devices;
+        }
+
+        // smaller pageable transfers go straight through cudaMemcpyAsync: waking the copy workers costs more than the driver's staging
+        constexpr long long kBounceMinFloats = 1 << 20;
+
+        struct RestoreDevice
+        {
+            int device;
+            ~RestoreDevice() { cudaSetDevice( device ); }
+        };
+
+        // One device's share of a staged call: units [begin, end) (rows or positions), issued chunk by chunk.
+        struct Shard
+        {
+            DeviceContext* ctx = nullptr;
+            long long begin = 0, end = 0, next = 0;
+            int slot = 0;
+            bool used[2] = { false, false };
+        };
 
         OutputMinMax GenGrid( const Generator* root, const GridCall& call, float* out )
         {
@@ -599,55 +863,92 @@ namespace FastNoise
                     return failed;
                 }
                 if( d ) rows *= call.count[d];
+                // same limit as the reference, whose index arithmetic is 32-bit [Generator.inl:150]
+                if( rows * call.count[0] >= 0x80000000ll )
+                {
+                    SetLastError( "grid has 2^31 or more points; use the slab entry points of FastNoise_B200.h" );
+                    return failed;
+                }
             }
             const long long nx = call.count[0];
-            if( rows * nx >= 0x80000000ll )
-            {
-                // same limit as the reference, whose index arithmetic is 32-bit [Generator.inl:150]
-                SetLastError( "grid has 2^31 or more points; use the slab entry points of FastNoise_B200.h" );
-                return failed;
-            }
             if( !out )
             {
                 SetLastError( "output pointer is null" );
                 return failed;
             }
 
-            ThreadContext& ctx = tContext;
-            if( !ctx.Ensure() ) return failed;
-            if( !Check( cudaMemsetAsync( ctx.minMax, 0, 2 * sizeof( unsigned ), ctx.compute ), "cudaMemsetAsync" ) ) return failed;
+            int current = 0;
+            if( !Check( cudaGetDevice( &current ), "cudaGetDevice" ) ) return failed;
+            RestoreDevice restore { current };
+            unsigned keys[2] = { 0, 0 };
 
-            OutputMinMax mm;
-            if( IsDevicePointer( out ) )
+            const Memory where = Classify( out );
+            if( where == Memory::Device )
             {
-                if( LaunchGridRows( root, call, out, 0, (unsigned long long)rows, ctx.minMax, ctx.compute ) != 0 ) return failed;
-                return ReadMinMax( ctx, mm ) ? mm : failed;
+                DeviceContext* ctx = tContexts.Get( current );
+                if( !ctx ) return failed;
+                if( !OrderAfterCaller( *ctx ) ) return failed;
+                if( !Check( cudaMemsetAsync( ctx->minMax, 0, 2 * sizeof( unsigned ), ctx->compute ), "cudaMemsetAsync" ) ) return failed;
+                if( LaunchGridRows( root, call, out, 0, (unsigned long long)rows, ctx->minMax, ctx->compute ) != 0 ) return failed;
+                return ReadMinMax( *ctx, keys ) ? DecodeMinMax( keys ) : failed;
             }
 
-            // host destination: rows are generated chunk by chunk into two device buffers; the D2H copy of
-            // chunk i runs on its own stream while chunk i+1 is being computed.
-            const long long chunkRows = std::max<long long>( 1, std::min<long long>( rows, (long long)( ChunkFloats() / (std::size_t)nx ) ) );
-            if( !ctx.EnsureOut( (std::size_t)( chunkRows * nx ) ) ) return failed;
-
-            int slot = 0;
-            bool used[2] = { false, false };
-            for( long long row = 0; row < rows; row += chunkRows, slot ^= 1 )
+            // host destination: every device generates a contiguous share of the rows chunk by chunk into two device buffers; the D2H
+            // copy of chunk i runs on its own stream while chunk i+1 is being computed. Pageable destinations are reached through
+            // pinned bounce buffers and the copy workers.
+            const bool pageable = where == Memory::Pageable && rows * nx >= kBounceMinFloats && EnvInt( "FASTNOISE2_B200_BOUNCE", 1 ) != 0;
+            const std::vector<int> devices = FanoutDevices( current, (unsigned long long)( rows * nx ) );
+            const long long chunkRows = std::max<long long>( 1, std::min<long long>( ( rows + (long long)devices.size() - 1 ) / (long long)devices.size(), (long long)( ChunkFloats() / (std::size_t)nx ) ) );
+            std::vector<Shard> shards( devices.size() );
+            for( std::size_t i = 0; i < devices.size(); i++ )
             {
-                const long long n = std::min( chunkRows, rows - row );
-                if( used[slot] && !Check( cudaStreamWaitEvent( ctx.compute, ctx.drained[slot], 0 ), "cudaStreamWaitEvent" ) ) return failed;
-                if( LaunchGridRows( root, call, ctx.outBuf[slot], (unsigned long long)row, (unsigned long long)n, ctx.minMax, ctx.compute ) != 0 ) return failed;
-                if( !Check( cudaEventRecord( ctx.computed[slot], ctx.compute ), "cudaEventRecord" ) ||
-                    !Check( cudaStreamWaitEvent( ctx.copyOut, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" ) ||
-                    !Check( cudaMemcpyAsync( out + row * nx, ctx.outBuf[slot], (std::size_t)( n * nx ) * sizeof( float ), cudaMemcpyDeviceToHost, ctx.copyOut ), "cudaMemcpyAsync(D2H)" ) ||
-                    !Check( cudaEventRecord( ctx.drained[slot], ctx.copyOut ), "cudaEventRecord" ) )
+                Shard& s = shards[i];
+                s.begin = s.next = rows * (long long)i / (long long)devices.size();
+                s.end = rows * (long long)( i + 1 ) / (long long)devices.size();
+                s.ctx = tContexts.Get( devices[i] );
+                if( !s.ctx || !s.ctx->EnsureOut( (std::size_t)( chunkRows * nx ) ) ) return failed;
+                if( pageable && !s.ctx->EnsureBounce( (std::size_t)( chunkRows * nx ) ) ) return failed;
+                if( !Check( cudaMemsetAsync( s.ctx->minMax, 0, 2 * sizeof( unsigned ), s.ctx->compute ), "cudaMemsetAsync" ) ) return failed;
+            }
+
+            bool ok = true;
+            for( bool work = true; work && ok; )
+            {
+                work = false;
+                for( Shard& s : shards )
                 {
-                    return failed;
+                    if( s.next >= s.end ) continue;
+                    work = true;
+                    DeviceContext& ctx = *s.ctx;
+                    const long long row = s.next, n = std::min( chunkRows, s.end - row );
+                    const int slot = s.slot;
+                    const std::size_t bytes = (std::size_t)( n * nx ) * sizeof( float );
+                    ok = Check( cudaSetDevice( ctx.device ), "cudaSetDevice" );
+                    if( ok && s.used[slot] ) ok = Check( cudaStreamWaitEvent( ctx.compute, ctx.drained[slot], 0 ), "cudaStreamWaitEvent" );
+                    ok = ok && LaunchGridRows( root, call, ctx.outBuf[slot], (unsigned long long)row, (unsigned long long)n, ctx.minMax, ctx.compute ) == 0;
+                    if( ok && pageable ) ctx.bounceBusy[slot].Wait(); // the workers have emptied this slot's bounce buffer
+                    float* target = pageable ? ctx.bounce[slot] : out + row * nx;
+                    ok = ok && Check( cudaEventRecord( ctx.computed[slot], ctx.compute ), "cudaEventRecord" ) &&
+                         Check( cudaStreamWaitEvent( ctx.copyOut, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" ) &&
+                         Check( cudaMemcpyAsync( target, ctx.outBuf[slot], bytes, cudaMemcpyDeviceToHost, ctx.copyOut ), "cudaMemcpyAsync(D2H)" ) &&
+                         Check( cudaEventRecord( ctx.drained[slot], ctx.copyOut ), "cudaEventRecord" );
+                    if( ok && pageable ) CopyPool::Get().Submit( ctx.drained[slot], (const char*)ctx.bounce[slot], (char*)( out + row * nx ), bytes, ctx.bounceBusy[slot] );
+                    s.used[slot] = true;
+                    s.slot ^= 1;
+                    s.next += n;
+                    if( !ok ) break;
                 }
-                used[slot] = true;
             }
-            if( !ReadMinMax( ctx, mm ) ) return failed;
-            if( !Check( cudaStreamSynchronize( ctx.copyOut ), "cudaStreamSynchronize" ) ) return failed;
-            return mm;
+            // drain every device even after a failure: the workers and DMA engines still reference the caller's buffer
+            for( Shard& s : shards )
+            {
+                if( !s.ctx ) continue;
+                cudaSetDevice( s.ctx->device );
+                if( ok ) ok = ReadMinMax( *s.ctx, keys );
+                if( !Check( cudaStreamSynchronize( s.ctx->copyOut ), "cudaStreamSynchronize" ) ) ok = false;
+                for( CopyPool::Ticket& t : s.ctx->bounceBusy ) t.Wait();
+            }
+            return ok ? DecodeMinMax( keys ) : failed;
         }
 
         OutputMinMax GenPositions( const Generator* root, int dims, float* out, long long count, const float* const pos[4], const float offset[4], int seed )
@@ -668,70 +969,115 @@ namespace FastNoise
                 }
             }
 
-            ThreadContext& ctx = tContext;
-            if( !ctx.Ensure() ) return failed;
-            if( !Check( cudaMemsetAsync( ctx.minMax, 0, 2 * sizeof( unsigned ), ctx.compute ), "cudaMemsetAsync" ) ) return failed;
+            int current = 0;
+            if( !Check( cudaGetDevice( &current ), "cudaGetDevice" ) ) return failed;
+            RestoreDevice restore { current };
+            unsigned keys[2] = { 0, 0 };
 
-            const bool outOnDevice = IsDevicePointer( out );
+            const Memory outWhere = Classify( out );
+            const bool outOnDevice = outWhere == Memory::Device;
             bool inOnDevice = true;
-            for( int d = 0; d < dims; d++ ) inOnDevice = inOnDevice && IsDevicePointer( pos[d] );
+            for( int d = 0; d < dims; d++ ) inOnDevice = inOnDevice && Classify( pos[d] ) == Memory::Device;
 
-            OutputMinMax mm;
             if( outOnDevice && inOnDevice )
             {
-                if( LaunchPositions( root, dims, out, (unsigned long long)count, pos, offset, seed, ctx.minMax, ctx.compute ) != 0 ) return failed;
-                return ReadMinMax( ctx, mm ) ? mm : failed;
+                DeviceContext* ctx = tContexts.Get( current );
+                if( !ctx ) return failed;
+                if( !OrderAfterCaller( *ctx ) ) return failed;
+                if( !Check( cudaMemsetAsync( ctx->minMax, 0, 2 * sizeof( unsigned ), ctx->compute ), "cudaMemsetAsync" ) ) return failed;
+                if( LaunchPositions( root, dims, out, (unsigned long long)count, pos, offset, seed, ctx->minMax, ctx->compute ) != 0 ) return failed;
+                return ReadMinMax( *ctx, keys ) ? DecodeMinMax( keys ) : failed;
             }
 
-            // staged pipeline: H2D of chunk i+1 (copyIn), kernel of chunk i (compute), D2H of chunk i-1 (copyOut)
-            const long long chunk = std::min<long long>( count, (long long)( ChunkFloats() / 2 ) & ~3ll );
-            if( !outOnDevice && !ctx.EnsureOut( (std::size_t)chunk ) ) return failed;
-            if( !inOnDevice && !ctx.EnsureIn( (std::size_t)chunk, dims ) ) return failed;
-
-            int slot = 0;
-            bool used[2] = { false, false };
-            for( long long first = 0; first < count; first += chunk, slot ^= 1 )
+            // staged pipeline per device: H2D of chunk i+1 (copyIn), kernel of chunk i (compute), D2H of chunk i-1 (copyOut).
+            // Device-resident arrays on either side pin the call to the current device.
+            const bool pageable = outWhere == Memory::Pageable && count >= kBounceMinFloats && EnvInt( "FASTNOISE2_B200_BOUNCE", 1 ) != 0;
+            const std::vector<int> devices = ( outOnDevice || inOnDevice ) ? std::vector<int> { current } : FanoutDevices( current, (unsigned long long)count );
+            const long long perDevice = ( count + (long long)devices.size() - 1 ) / (long long)devices.size();
+            const long long chunk = std::max<long long>( 4, std::min<long long>( ( perDevice + 3 ) & ~3ll, (long long)( ChunkFloats() / 2 ) & ~3ll ) );
+            std::vector<Shard> shards( devices.size() );
+            for( std::size_t i = 0; i < devices.size(); i++ )
             {
-                const long long n = std::min( chunk, count - first );
-                const float* devPos[4] = { nullptr, nullptr, nullptr, nullptr };
-                if( inOnDevice )
-                {
-                    for( int d = 0; d < dims; d++ ) devPos[d] = pos[d] + first;
-                }
-                else
-                {
-                    // the slot's input buffers are free once the kernel that last read them has finished
-                    if( used[slot] && !Check( cudaStreamWaitEvent( ctx.copyIn, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" ) ) return failed;
-                    for( int d = 0; d < dims; d++ )
-                    {
-                        if( !Check( cudaMemcpyAsync( ctx.inBuf[slot][d], pos[d] + first, (std::size_t)n * sizeof( float ), cudaMemcpyHostToDevice, ctx.copyIn ), "cudaMemcpyAsync(H2D)" ) ) return failed;
-                        devPos[d] = ctx.inBuf[slot][d];
-                    }
-                    if( !Check( cudaEventRecord( ctx.uploaded[slot], ctx.copyIn ), "cudaEventRecord" ) ||
-                        !Check( cudaStreamWaitEvent( ctx.compute, ctx.uploaded[slot], 0 ), "cudaStreamWaitEvent" ) ) return failed;
-                }
-
-                float* devOut = outOnDevice ? out + first : ctx.outBuf[slot];
-                if( !outOnDevice && used[slot] && !Check( cudaStreamWaitEvent( ctx.compute, ctx.drained[slot], 0 ), "cudaStreamWaitEvent" ) ) return failed;
-                if( LaunchPositions( root, dims, devOut, (unsigned long long)n, devPos, offset, seed, ctx.minMax, ctx.compute ) != 0 ) return failed;
-                if( !Check( cudaEventRecord( ctx.computed[slot], ctx.compute ), "cudaEventRecord" ) ) return failed;
-                if( !outOnDevice )
-                {
-                    if( !Check( cudaStreamWaitEvent( ctx.copyOut, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" ) ||
-                        !Check( cudaMemcpyAsync( out + first, devOut, (std::size_t)n * sizeof( float ), cudaMemcpyDeviceToHost, ctx.copyOut ), "cudaMemcpyAsync(D2H)" ) ||
-                        !Check( cudaEventRecord( ctx.drained[slot], ctx.copyOut ), "cudaEventRecord" ) ) return failed;
-                }
-                used[slot] = true;
+                Shard& s = shards[i];
+                s.begin = s.next = std::min( count, ( ( count * (long long)i / (long long)devices.size() ) + 3 ) & ~3ll ); // 16-byte aligned shares
+                s.end = i + 1 == devices.size() ? count : std::min( count, ( ( count * (long long)( i + 1 ) / (long long)devices.size() ) + 3 ) & ~3ll );
+                s.ctx = tContexts.Get( devices[i] );
+                if( !s.ctx ) return failed;
+                if( !outOnDevice && !s.ctx->EnsureOut( (std::size_t)chunk ) ) return failed;
+                if( !inOnDevice && !s.ctx->EnsureIn( (std::size_t)chunk, dims ) ) return failed;
+                if( pageable && !s.ctx->EnsureBounce( (std::size_t)chunk ) ) return failed;
+                if( ( outOnDevice || inOnDevice ) && !OrderAfterCaller( *s.ctx ) ) return failed;
+                if( !Check( cudaMemsetAsync( s.ctx->minMax, 0, 2 * sizeof( unsigned ), s.ctx->compute ), "cudaMemsetAsync" ) ) return failed;
             }
-            if( !ReadMinMax( ctx, mm ) ) return failed;
-            if( !Check( cudaStreamSynchronize( ctx.copyOut ), "cudaStreamSynchronize" ) ) return failed;
-            if( !Check( cudaStreamSynchronize( ctx.copyIn ), "cudaStreamSynchronize" ) ) return failed;
-            return mm;
+
+            bool ok = true;
+            for( bool work = true; work && ok; )
+            {
+                work = false;
+                for( Shard& s : shards )
+                {
+                    if( s.next >= s.end ) continue;
+                    work = true;
+                    DeviceContext& ctx = *s.ctx;
+                    const long long first = s.next, n = std::min( chunk, s.end - first );
+                    const int slot = s.slot;
+                    ok = Check( cudaSetDevice( ctx.device ), "cudaSetDevice" );
+                    const float* devPos[4] = { nullptr, nullptr, nullptr, nullptr };
+                    if( inOnDevice )
+                    {
+                        for( int d = 0; d < dims; d++ ) devPos[d] = pos[d] + first;
+                        if( ok && !outOnDevice && s.used[slot] ) ok = Check( cudaStreamWaitEvent( ctx.compute, ctx.drained[slot], 0 ), "cudaStreamWaitEvent" );
+                    }
+                    else
+                    {
+                        // the slot's input buffers are free once the kernel that last read them has finished
+                        if( ok && s.used[slot] ) ok = Check( cudaStreamWaitEvent( ctx.copyIn, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" );
+                        for( int d = 0; ok && d < dims; d++ )
+                        {
+                            ok = Check( cudaMemcpyAsync( ctx.inBuf[slot][d], pos[d] + first, (std::size_t)n * sizeof( float ), cudaMemcpyHostToDevice, ctx.copyIn ), "cudaMemcpyAsync(H2D)" );
+                            devPos[d] = ctx.inBuf[slot][d];
+                        }
+                        ok = ok && Check( cudaEventRecord( ctx.uploaded[slot], ctx.copyIn ), "cudaEventRecord" ) &&
+                             Check( cudaStreamWaitEvent( ctx.compute, ctx.uploaded[slot], 0 ), "cudaStreamWaitEvent" );
+                        if( ok && !outOnDevice && s.used[slot] ) ok = Check( cudaStreamWaitEvent( ctx.compute, ctx.drained[slot], 0 ), "cudaStreamWaitEvent" );
+                    }
+
+                    float* devOut = outOnDevice ? out + first : ctx.outBuf[slot];
+                    ok = ok && LaunchPositions( root, dims, devOut, (unsigned long long)n, devPos, offset, seed, ctx.minMax, ctx.compute ) == 0;
+                    ok = ok && Check( cudaEventRecord( ctx.computed[slot], ctx.compute ), "cudaEventRecord" );
+                    if( ok && !outOnDevice )
+                    {
+                        if( pageable ) ctx.bounceBusy[slot].Wait();
+                        float* target = pageable ? ctx.bounce[slot] : out + first;
+                        ok = Check( cudaStreamWaitEvent( ctx.copyOut, ctx.computed[slot], 0 ), "cudaStreamWaitEvent" ) &&
+                             Check( cudaMemcpyAsync( target, devOut, (std::size_t)n * sizeof( float ), cudaMemcpyDeviceToHost, ctx.copyOut ), "cudaMemcpyAsync(D2H)" ) &&
+                             Check( cudaEventRecord( ctx.drained[slot], ctx.copyOut ), "cudaEventRecord" );
+                        if( ok && pageable ) CopyPool::Get().Submit( ctx.drained[slot], (const char*)ctx.bounce[slot], (char*)( out + first ), (std::size_t)n * sizeof( float ), ctx.bounceBusy[slot] );
+                    }
+                    s.used[slot] = true;
+                    s.slot ^= 1;
+                    s.next += n;
+                    if( !ok ) break;
+                }
+            }
+            for( Shard& s : shards )
+            {
+                if( !s.ctx ) continue;
+                cudaSetDevice( s.ctx->device );
+                if( ok ) ok = ReadMinMax( *s.ctx, keys );
+                if( !Check( cudaStreamSynchronize( s.ctx->copyOut ), "cudaStreamSynchronize" ) ) ok = false;
+                if( !Check( cudaStreamSynchronize( s.ctx->copyIn ), "cudaStreamSynchronize" ) ) ok = false;
+                for( CopyPool::Ticket& t : s.ctx->bounceBusy ) t.Wait();
+            }
+            return ok ? DecodeMinMax( keys ) : failed;
         }
 
         cudaStream_t ThreadStream()
         {
-            return tContext.Ensure() ? tContext.compute : nullptr;
+            int current = 0;
+            if( cudaGetDevice( &current ) != cudaSuccess ) return nullptr;
+            DeviceContext* ctx = tContexts.Get( current );
+            return ctx ? ctx->compute : nullptr;
         }
 
         bool DeviceAvailable()

@@ -1,6 +1,7 @@
 // fastnoise2_b200 internal -- backend entry points used by the C ABI and the Generator virtuals.
 #pragma once
 #include <string>
+#include <vector>
 
 #include <FastNoise/Generators/Generator.h>
 #include "internal.h"
@@ -19,7 +20,7 @@ namespace FastNoise
             float off[4];
             float step[4];
             int count[4];
-            unsigned rowBegin, total, vecStore, pad;
+            unsigned rowBegin, total, vecStore, groups;
             FastDivHost divX, divY, divZ;
         };
 
@@ -27,7 +28,7 @@ namespace FastNoise
         {
             float xFreq, yFreq, xMul, yMul;
             int xSize, ySize;
-            unsigned rowBegin, total, vecStore, pad[3];
+            unsigned rowBegin, total, vecStore, groups, pad[2];
             FastDivHost divX;
         };
 
@@ -35,7 +36,7 @@ namespace FastNoise
         {
             const float* pos[4];
             float off[4];
-            unsigned long long count;
+            unsigned long long count, groups;
             unsigned vecIO, pad;
         };
 
@@ -61,7 +62,9 @@ namespace FastNoise
         OutputMinMax DecodeMinMax( const unsigned keys[2] );
 
         std::string KernelSource( const Generator* root, int kind, int pointsPerThread );
+        std::vector<float> KernelParams( const Generator* root, int kind, int pointsPerThread ); ///< current values of the kernel's TreeParams argument
         int PrepareOffline( const Generator* root, int kind, int pointsPerThread ); ///< lower + NVRTC into the disk cache; needs no GPU
+        int PrepareAll( const Generator* root, int kind ); ///< PrepareOffline for every points-per-thread variant a launch can pick
 
         /// Rows [rowBegin, rowBegin + rowCount) of the full grid into deviceOut (first element = first point of rowBegin). 0 or FNB200_E*.
         int LaunchGridRows( const Generator* root, const GridCall& call, float* deviceOut, unsigned long long rowBegin, unsigned long long rowCount,

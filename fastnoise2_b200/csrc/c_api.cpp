@@ -209,7 +209,7 @@ extern "C"
     {
         const char* v = std::getenv( "FASTNOISE2_B200_PPT" );
         int p = v && *v ? std::atoi( v ) : 4;
-        return p >= 4 ? 4 : ( p >= 2 ? 2 : 1 );
+        return p >= 4 ? 4 : 1;
     }
 
     int fnb200Prepare( const void* node, int kind )
@@ -219,7 +219,15 @@ extern "C"
             Impl::SetLastError( "fnb200Prepare: bad node or kind" );
             return FNB200_EINVAL;
         }
-        return Impl::PrepareOffline( Gen( node ), kind, DefaultPpt() );
+        return Impl::PrepareAll( Gen( node ), kind );
+    }
+
+    long fnb200GetKernelParams( const void* node, int kind, float* buf, long bufCount )
+    {
+        if( !node || !Impl::EntryKindValid( kind ) ) return FNB200_EINVAL;
+        const std::vector<float> params = Impl::KernelParams( Gen( node ), kind, DefaultPpt() );
+        for( long i = 0; buf && i < bufCount && i < (long)params.size(); i++ ) buf[i] = params[i];
+        return (long)params.size();
     }
 
     long fnb200GetKernelSource( const void* node, int kind, char* buf, long bufSize )

@@ -21,7 +21,7 @@ namespace fn2
         u32 rowBegin;   // first x-row of this launch, counted over the FULL grid (row = linear index / count[0])
         u32 total;      // points in this launch ( < 2^31 )
         u32 vecStore;   // 1: output pointer is 16-byte aligned, vector stores allowed
-        u32 pad;
+        u32 groups;     // total / points per thread: the grid-stride loop bound
         FastDiv divX, divY, divZ;
     };
 
@@ -32,7 +32,8 @@ namespace fn2
         u32 rowBegin;
         u32 total;
         u32 vecStore;
-        u32 pad[3];
+        u32 groups;
+        u32 pad[2];
         FastDiv divX;
     };
 
@@ -41,6 +42,7 @@ namespace fn2
         const float* pos[4];
         float off[4];
         unsigned long long count;
+        unsigned long long groups; // ceil( count / points per thread )
         u32 vecIO; // 1: out and every position array are 16-byte aligned
         u32 pad;
     };

@@ -32,10 +32,11 @@ namespace FastNoise
         {
             std::string source;  ///< complete CUDA translation unit (device library + generated tree + entry kernel)
             std::string error;   ///< non-empty if the tree cannot be lowered
-            int pointsPerThread; ///< 1, 2 or 4 (only the grid/positions index math depends on it)
+            int pointsPerThread; ///< 1 or 4 (only the grid/positions index math depends on it)
+            std::vector<float> params; ///< parameter mode: the values of the kernel's TreeParams argument, in slot order
         };
         /// Generates the CUDA source that evaluates the tree rooted at `root` for one entry kind.
-        LoweredProgram LowerTree( const Generator* root, int entryKind, int pointsPerThread, int mathMode );
+        LoweredProgram LowerTree( const Generator* root, int entryKind, int pointsPerThread, int mathMode, bool paramMode );
         const char* DeviceLibrarySource();
 
         // backend.cpp

@@ -19,6 +19,8 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <algorithm>
+#include <vector>
 #include <unordered_map>
 
 #include "internal.h"
@@ -93,6 +95,19 @@ namespace
         std::set<std::pair<int, int>> genDone, warpDone;
         std::string error;
         int depth = 0;
+        bool paramMode = false;     // float node parameters travel as kernel arguments (tp[k]) instead of literals
+        std::vector<float> params;  // their values, in slot order
+
+        // A float node parameter (or a value folded from node parameters on the host): a literal, or -- in parameter mode -- a
+        // slot of the kernel's TreeParams argument, so that one compiled kernel serves every tree of the same shape. Values the
+        // emitter LOOKS at to choose between code shapes (a zero weighted strength, a clamp bound that cannot be NaN ...) still
+        // change the text, and with it the kernel, when the choice changes.
+        std::string Par( float v )
+        {
+            if( !paramMode ) return Lit( v );
+            params.push_back( v );
+            return "tp[" + std::to_string( params.size() - 1 ) + "]";
+        }
 
         int IndexOf( const Generator* g )
         {
@@ -127,7 +142,7 @@ namespace
                 {
                     std::string body = Body( g, k, dim ); // emits the children first
                     out << "// " << g->GetMetadata().name << " " << dim << "D\n"
-                        << "FN2_DI F n" << k << "_" << dim << "( int seed, " << PosDecl( dim ) << " )\n{\n" << body << "}\n\n";
+                        << "FN2_DI F n" << k << "_" << dim << "( int seed, " << PosDecl( dim ) << ", FN2_TP )\n{\n" << body << "}\n\n";
                 }
                 --depth;
             }
@@ -137,7 +152,7 @@ namespace
         // call expression of a required source
         std::string Call( const Generator* g, int dim, const std::string& seed, const std::string& pos )
         {
-            return Gen( g, dim ) + "( " + seed + ", " + pos + " )";
+            return Gen( g, dim ) + "( " + seed + ", " + pos + ", tp )";
         }
 
         std::string Src( const Generator* owner, int lookup, int dim, const std::string& seed, const std::string& pos )
@@ -150,7 +165,7 @@ namespace
         {
             const Impl::NodeState::Hybrid& h = owner->State().hybrids[hybrid];
             if( h.node ) return Call( h.node.get(), dim, seed, pos );
-            return Lit( h.constant );
+            return Par( h.constant );
         }
 
         static bool HybIsConst( const Generator* owner, int hybrid, float value )
@@ -202,16 +217,17 @@ namespace
         }
 
         // ScaleOutput [BasicGenerators.inl:27-30]: fma( (1/(max-min)) * rangeScale, value - min, rangeMin ), factor folded on the host in float
-        static std::string Range( const Impl::NodeState& s, const std::string& value, float nativeMin, float nativeMax )
+        std::string Range( const Impl::NodeState& s, const std::string& value, float nativeMin, float nativeMax )
         {
             float k = ( 1.0f / ( nativeMax - nativeMin ) ) * s.f[F_RangeScale];
-            return "fn2::fma_( " + Lit( k ) + ", " + value + " - " + Lit( nativeMin ) + ", " + Lit( s.f[F_RangeMin] ) + " )";
+            return "fn2::fma_( " + Par( k ) + ", " + value + " - " + Lit( nativeMin ) + ", " + Par( s.f[F_RangeMin] ) + " )";
         }
 
-        static std::string ScalePositions( const Impl::NodeState& s, int dim )
+        std::string ScalePositions( const Impl::NodeState& s, int dim )
         {
             std::string code;
-            for( int d = 0; d < dim; d++ ) code += std::string( "    " ) + kAxis[d] + " *= " + Lit( s.f[F_Frequency] ) + ";\n";
+            const std::string f = Par( s.f[F_Frequency] );
+            for( int d = 0; d < dim; d++ ) code += std::string( "    " ) + kAxis[d] + " *= " + f + ";\n";
             return code;
         }
 
@@ -232,12 +248,12 @@ namespace
 
             const Impl::NodeState& s = g->State();
             out << "// " << g->GetMetadata().name << "::Warp " << dim << "D\n"
-                << "FN2_DI F " << name << "( int seed, F warpAmp, " << PosDecl( dim, "F ", "s" ) << ", " << PosDecl( dim, "F& " ) << " )\n{\n";
+                << "FN2_DI F " << name << "( int seed, F warpAmp, " << PosDecl( dim, "F ", "s" ) << ", " << PosDecl( dim, "F& " ) << ", FN2_TP )\n{\n";
             if( s.nodeId == N_DomainWarpGradient )
             {
                 out << AddSeedOffset( s ) // Warp() adds the offset itself [DomainWarp.inl:35,79,136]
                     << "    return fn2::warp_gradient" << dim << "( seed, warpAmp, " << Pos( dim, "s" ) << ", " << Pos( dim );
-                for( int d = 0; d < dim; d++ ) out << ", " << Lit( s.f[F_K0 + d] );
+                for( int d = 0; d < dim; d++ ) out << ", " << Par( s.f[F_K0 + d] );
                 out << " );\n";
             }
             else
@@ -254,7 +270,7 @@ namespace
                       { 48.80058117543753f, (float)( 115.21625311930542 / 1.4142135623730951 ) } } };
                 if( !super ) out << AddSeedOffset( s );
                 out << "    return fn2::warp_simplex" << dim << "<" << ( super ? 1 : 0 ) << ", " << scheme << ">( seed, warpAmp, " << Pos( dim, "s" ) << ", " << Pos( dim );
-                for( int d = 0; d < dim; d++ ) out << ", " << Lit( kBound[super ? 1 : 0][dim - 2][scheme] * s.f[F_K0 + d] );
+                for( int d = 0; d < dim; d++ ) out << ", " << Par( kBound[super ? 1 : 0][dim - 2][scheme] * s.f[F_K0 + d] );
                 out << " );\n";
             }
             out << "}\n\n";
@@ -300,7 +316,7 @@ namespace
             switch( s.nodeId )
             {
             case N_Constant:
-                b << "    return " << Lit( s.f[F_K0] ) << ";\n";
+                b << "    return " << Par( s.f[F_K0] ) << ";\n";
                 break;
 
             case N_White:
@@ -319,7 +335,7 @@ namespace
                 b << "    F r = 0.0f;\n";
                 for( int d = 0; d < dim; d++ )
                 {
-                    b << "    r = fn2::fma_( " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ", " << Lit( s.f[F_K0 + d] ) << ", r );\n";
+                    b << "    r = fn2::fma_( " << kAxis[d] << " + " << Hyb( g, d, dim, "seed", P ) << ", " << Par( s.f[F_K0 + d] ) << ", r );\n";
                 }
                 b << "    return r;\n";
                 break;
@@ -410,7 +426,7 @@ namespace
                 std::string C = Pos( dim, "c" );
                 b << "    F " << C << ";\n";
                 b << "    fn2::cellular_lookup" << D << "<" << df << ", " << ( sizeJ ? "true" : "false" ) << ">( seed, " << P << ", jitter, sizeJitter, minkowskiP, " << C << " );\n";
-                b << "    return " << Src( g, 0, dim, "fn2::iadd( sourceSeed, 1 )", Scaled( dim, Lit( s.f[F_Scale] ), "c" ) ) << ";\n";
+                b << "    return " << Src( g, 0, dim, "fn2::iadd( sourceSeed, 1 )", Scaled( dim, Par( s.f[F_Scale] ), "c" ) ) << ";\n";
                 break;
             }
 
@@ -435,7 +451,10 @@ namespace
                     b << "        seed = fn2::iadd( seed, 1 );\n";
                     if( weighted ) b << "        amp *= fn2::lerp( 1.0f, " << ( ridged ? "1.0f - noise" : "( noise + 1.0f ) * 0.5f" ) << ", weightedStrength );\n";
                     b << "        amp *= gain;\n";
-                    for( int d = 0; d < dim; d++ ) b << "        " << kAxis[d] << " *= " << Lit( s.f[F_K0] ) << ";\n";
+                    {
+                        const std::string lacunarity = Par( s.f[F_K0] );
+                        for( int d = 0; d < dim; d++ ) b << "        " << kAxis[d] << " *= " << lacunarity << ";\n";
+                    }
                     b << "        noise = " << sample << ";\n";
                     b << "        sum += " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
                     b << "    }\n";
@@ -458,7 +477,7 @@ namespace
                 std::string warp = Warp( g, dim );
                 b << "    const int sourceSeed = seed;\n" << AddSeedOffset( s );
                 b << "    const F warpAmp = " << Hyb( g, 0, dim, "sourceSeed", P ) << ";\n";
-                b << "    " << warp << "( seed, warpAmp, " << Scaled( dim, Lit( s.f[F_Frequency] ) ) << ", " << P << " );\n";
+                b << "    " << warp << "( seed, warpAmp, " << Scaled( dim, Par( s.f[F_Frequency] ) ) << ", " << P << ", tp );\n";
                 b << "    return " << Src( g, 0, dim, "sourceSeed", P ) << ";\n";
                 break;
             }
@@ -481,20 +500,20 @@ namespace
                 std::string N = independent ? Pos( dim, "n" ) : P; // position the frequency is applied to
                 b << "    F amp = " << Hyb( warpNode, 0, dim, "seed", P ) << ";\n";
                 if( weighted ) b << "    const F weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    F freq = " << Lit( ws.f[F_Frequency] ) << ";\n";
+                b << "    F freq = " << Par( ws.f[F_Frequency] ) << ";\n";
                 b << "    int seedInc = seed;\n";
                 b << "    const F gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
                 if( independent ) for( int d = 0; d < dim; d++ ) b << "    const F n" << kAxis[d] << " = " << kAxis[d] << ";\n";
-                b << "    F strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
+                b << "    F strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << ", tp );\n";
                 if( octaves > 1 )
                 {
                     b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
                     if( weighted ) b << "        strength = fn2::fast_length_sqrt( strength );\n";
                     b << "        seedInc = fn2::iadd( seedInc, 1 );\n";
-                    b << "        freq *= " << Lit( s.f[F_K0] ) << ";\n";
+                    b << "        freq *= " << Par( s.f[F_K0] ) << ";\n";
                     if( weighted ) b << "        amp *= fn2::lerp( 1.0f, 1.0f - strength, weightedStrength );\n";
                     b << "        amp *= gain;\n";
-                    b << "        strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << " );\n";
+                    b << "        strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << ", tp );\n";
                     b << "    }\n";
                 }
                 b << "    (void)strength;\n";
@@ -540,9 +559,21 @@ namespace
                 b << "    const F a = " << neg << Src( g, 0, dim, "seed", P ) << ";\n";
                 b << "    const F b = " << neg << Hyb( g, 0, dim, "seed", P ) << ";\n";
                 // |smoothness| is +0 or larger: only a NaN can make the two forms differ
-                b << "    const F smoothness = " << MinMax( true, "0x1p-126f", "fn2::abs_( " + Hyb( g, 1, dim, "seed", P ) + " )", HybClampSafe( g, 1, false ) && HybClampSafe( g, 1, true ) ) << ";\n";
-                b << "    F h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
-                b << "    h *= fn2::reciprocal( smoothness );\n";
+                const Impl::NodeState::Hybrid& sm = s.hybrids[1];
+                if( !sm.node && sm.constant == sm.constant )
+                {
+                    // constant smoothness: the clamp and the reciprocal are folded here, in the same float arithmetic
+                    const float smoothness = std::fmax( 0x1p-126f, std::fabs( sm.constant ) );
+                    b << "    const F smoothness = " << Par( smoothness ) << ";\n";
+                    b << "    F h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
+                    b << "    h *= " << Par( 1.0f / smoothness ) << ";\n";
+                }
+                else
+                {
+                    b << "    const F smoothness = " << MinMax( true, "0x1p-126f", "fn2::abs_( " + Hyb( g, 1, dim, "seed", P ) + " )", HybClampSafe( g, 1, false ) && HybClampSafe( g, 1, true ) ) << ";\n";
+                    b << "    F h = fn2::max_( smoothness - fn2::abs_( a - b ), 0.0f );\n";
+                    b << "    h *= fn2::reciprocal( smoothness );\n";
+                }
                 b << "    return " << neg << "fn2::fnma_( " << Lit( 1.0f / 6.0f ) << ", h * h * h * smoothness, " << MinMax( false, "a", "b", HybClampSafe( g, 0, false ) && HybClampSafe( g, 0, true ) ) << " );\n";
                 break;
             }
@@ -560,7 +591,7 @@ namespace
                 break;
 
             case N_DomainScale:
-                b << "    return " << Src( g, 0, dim, "seed", Scaled( dim, Lit( s.f[F_K0] ) ) ) << ";\n";
+                b << "    return " << Src( g, 0, dim, "seed", Scaled( dim, Par( s.f[F_K0] ) ) ) << ";\n";
                 break;
 
             case N_DomainOffset: // [Modifiers.inl:15-28] every offset is sampled at the un-offset position
@@ -580,12 +611,13 @@ namespace
                 }
                 else if( dim == 2 && ps == 0.0f && rs == 0.0f )
                 {
+                    const std::string sinYaw = Par( ys ), cosYaw = Par( yc );
                     b << "    return " << Src( g, 0, 2, "seed",
-                        "fn2::fnma_( y, " + Lit( ys ) + ", x * " + Lit( yc ) + " ), fn2::fma_( x, " + Lit( ys ) + ", y * " + Lit( yc ) + " )" ) << ";\n";
+                        "fn2::fnma_( y, " + sinYaw + ", x * " + cosYaw + " ), fn2::fma_( x, " + sinYaw + ", y * " + cosYaw + " )" ) << ";\n";
                 }
                 else if( dim == 2 )
                 {
-                    b << "    return " << Gen( g, 3 ) << "( seed, x, y, 0.0f );\n";
+                    b << "    return " << Gen( g, 3 ) << "( seed, x, y, 0.0f, tp );\n";
                 }
                 else
                 {
@@ -594,7 +626,7 @@ namespace
                     const float za = -ps, zb = pc * rs, zc = pc * rc;
                     auto row = [&]( float a, float bb, float c )
                     {
-                        return "fn2::fma_( x, " + Lit( a ) + ", fn2::fma_( y, " + Lit( bb ) + ", z * " + Lit( c ) + " ) )";
+                        return "fn2::fma_( x, " + Par( a ) + ", fn2::fma_( y, " + Par( bb ) + ", z * " + Par( c ) + " ) )";
                     };
                     b << "    return " << Src( g, 0, 3, "seed", row( xa, xb, xc ) + ", " + row( ya, yb, ycc ) + ", " + row( za, zb, zc ) ) << ";\n";
                 }
@@ -602,7 +634,7 @@ namespace
             }
 
             case N_DomainAxisScale:
-                for( int d = 0; d < dim; d++ ) b << "    " << kAxis[d] << " *= " << Lit( s.f[F_K0 + d] ) << ";\n";
+                for( int d = 0; d < dim; d++ ) b << "    " << kAxis[d] << " *= " << Par( s.f[F_K0 + d] ) << ";\n";
                 b << "    return " << Src( g, 0, dim, "seed", P ) << ";\n";
                 break;
 
@@ -614,10 +646,11 @@ namespace
             {
                 const float lo = s.f[F_K0], hi = s.f[F_K0 + 1];
                 b << "    F v = " << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    v = " << MinMax( false, "v", Lit( hi ), ClampSafe( hi, false ) ) << ";\n";
-                b << "    v = " << MinMax( true, "v", Lit( lo ), ClampSafe( lo, true ) ) << ";\n";
-                b << "    v -= " << Lit( lo ) << ";\n";
-                b << "    v *= " << Lit( 255.0f / ( hi - lo ) ) << ";\n";
+                const std::string loText = Par( lo );
+                b << "    v = " << MinMax( false, "v", Par( hi ), ClampSafe( hi, false ) ) << ";\n";
+                b << "    v = " << MinMax( true, "v", loText, ClampSafe( lo, true ) ) << ";\n";
+                b << "    v -= " << loText << ";\n";
+                b << "    v *= " << Par( 255.0f / ( hi - lo ) ) << ";\n";
                 b << "    const I byteVal = fn2::cvt_i( v );\n";
                 b << "    return fn2::bitsf( (int)0xff000000u | byteVal | fn2::shl( byteVal, 8 ) | fn2::shl( byteVal, 16 ) );\n";
                 break;
@@ -660,7 +693,7 @@ namespace
             case N_Terrace: // [Modifiers.inl:130-182]
             {
                 b << "    F source = " << Src( g, 0, dim, "seed", P ) << ";\n";
-                b << "    source *= " << Lit( s.f[F_K0] ) << ";\n";
+                b << "    source *= " << Par( s.f[F_K0] ) << ";\n";
                 b << "    F rounded = fn2::round_( source );\n";
                 const bool dynamic = (bool)s.hybrids[0].node;
                 if( dynamic || s.hybrids[0].constant != 0.0f )
@@ -671,13 +704,13 @@ namespace
                     b << "    diff = fn2::abs_( diff );\n";
                     b << "    diff = 0.5f - diff;\n";
                     if( dynamic ) b << "    diff *= 1.0f + fn2::reciprocal( smoothness );\n";
-                    else b << "    diff *= " << Lit( s.f[F_K0 + 2] ) << ";\n";
+                    else b << "    diff *= " << Par( s.f[F_K0 + 2] ) << ";\n";
                     b << "    diff = fn2::min_( diff, 0.5f );\n";
                     b << "    diff = fn2::select( diffSign, 0.5f - diff, diff - 0.5f );\n";
                     if( dynamic ) b << "    rounded = fn2::select( smoothness != 0.0f, rounded + diff, rounded );\n";
                     else b << "    rounded += diff;\n";
                 }
-                b << "    return rounded * " << Lit( s.f[F_K0 + 1] ) << ";\n";
+                b << "    return rounded * " << Par( s.f[F_K0 + 1] ) << ";\n";
                 break;
             }
 
@@ -741,17 +774,55 @@ namespace
     };
 
     // ------------------------------------------------------------------ entry kernels
-    // Entry kernels. A thread owns `ppt` consecutive points and evaluates them FN2_W at a time (FN2_W = 2: one fpair per two
-    // points, see fn2_device_pack.cuh); fn2::index_positions / lane_values / spill_lanes are the width-generic glue.
+    // Entry kernels are persistent: the launch fills the GPU once (backend.cpp sizes the grid to the resident blocks) and every
+    // thread walks the call's point groups with a grid stride, so the gradient tables are staged and the block min/max is reduced
+    // once per thread, not once per group. A group is `ppt` consecutive points of one x-row (4: rows are a multiple of 4 wide and
+    // the thread stores one 16-byte vector; 1: any width, a warp stores 32 consecutive floats), evaluated FN2_W at a time
+    // (FN2_W = 2: one fpair per two points, see fn2_device_pack.cuh).
+    const char* const kEntryHead = "( float* __restrict__ out, const fn2::";
+    std::string EntryOpen( const char* argsType, int ppt, bool wide )
+    {
+        std::ostringstream k;
+        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry" << kEntryHead << argsType
+          << " a, unsigned* __restrict__ mm, int seed, const FN2_GRID_CONSTANT fn2::TreeParams params )\n{\n"
+          << "    const float* __restrict__ tp = params.v;\n"
+          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
+          << "    bool any = false;\n"
+          << "    fn2::stage_tables();\n";
+        if( wide )
+        {
+            k << "    const unsigned long long stride = (unsigned long long)gridDim.x * FN2_BLOCK;\n"
+              << "    for( unsigned long long group = (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
+              << "        const unsigned long long first = group * " << ppt << "u;\n";
+        }
+        else
+        {
+            k << "    const unsigned stride = gridDim.x * FN2_BLOCK;\n"
+              << "    for( unsigned group = blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
+              << "        const unsigned first = group * " << ppt << "u;\n";
+        }
+        k << "        any = true;\n";
+        return k.str();
+    }
+
+    std::string EntryClose( int ppt )
+    {
+        std::ostringstream k;
+        k << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
+          << "            vmin = fn2::min_( vmin, v[p] );\n"
+          << "            vmax = fn2::max_( vmax, v[p] );\n"
+          << "        }\n"
+          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
+          << "    }\n"
+          << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n";
+        return k.str();
+    }
+
     std::string GridEntry( int dim, const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::GridArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
-          << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
-          << "    const bool valid = first < a.total;\n"
-          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
-          << "    fn2::stage_tables();\n"
-          << "    if( valid )\n    {\n"
+        k << EntryOpen( "GridArgs", ppt, false )
           << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
           << "        const unsigned ix = first - rowLocal * (unsigned)a.count[0];\n"
           << "        const unsigned row = rowLocal + a.rowBegin;\n";
@@ -780,28 +851,16 @@ namespace
           << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p += FN2_W )\n        {\n"
           << "            const F px = fn2::index_positions<F>( ix + p, a.step[0], a.off[0] );\n"
-          << "            fn2::spill_lanes( " << root << "( seed, " << Pos( dim, "p" ) << " ), v + p );\n"
+          << "            fn2::spill_lanes( " << root << "( seed, " << Pos( dim, "p" ) << ", tp ), v + p );\n"
           << "        }\n"
-          << "#pragma unroll\n"
-          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            vmin = fn2::min_( vmin, v[p] );\n"
-          << "            vmax = fn2::max_( vmax, v[p] );\n"
-          << "        }\n"
-          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
-          << "    }\n"
-          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+          << EntryClose( ppt );
         return k.str();
     }
 
     std::string TileEntry( const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::TileArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
-          << "    const unsigned first = ( blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
-          << "    const bool valid = first < a.total;\n"
-          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
-          << "    fn2::stage_tables();\n"
-          << "    if( valid )\n    {\n"
+        k << EntryOpen( "TileArgs", ppt, false )
           << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
           << "        const unsigned ix = first - rowLocal * (unsigned)a.xSize;\n"
           << "        const unsigned iy = rowLocal + a.rowBegin;\n"
@@ -815,28 +874,16 @@ namespace
           << "            const F xF = fn2::index_positions<F>( ix + p, a.xMul );\n"
           << "            const F px = fn2::cos_poly( xF ) * a.xFreq;\n"
           << "            const F pz = fn2::sin_poly( xF ) * a.xFreq;\n"
-          << "            fn2::spill_lanes( " << root << "( seed, px, py, pz, pw ), v + p );\n"
+          << "            fn2::spill_lanes( " << root << "( seed, px, py, pz, pw, tp ), v + p );\n"
           << "        }\n"
-          << "#pragma unroll\n"
-          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            vmin = fn2::min_( vmin, v[p] );\n"
-          << "            vmax = fn2::max_( vmax, v[p] );\n"
-          << "        }\n"
-          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
-          << "    }\n"
-          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+          << EntryClose( ppt );
         return k.str();
     }
 
     std::string PositionsEntry( int dim, const std::string& root, int ppt )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry( float* __restrict__ out, const fn2::PosArgs a, unsigned* __restrict__ mm, int seed )\n{\n"
-          << "    const unsigned long long first = ( (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x ) * " << ppt << "u;\n"
-          << "    const bool valid = first < a.count;\n"
-          << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
-          << "    fn2::stage_tables();\n"
-          << "    if( valid )\n    {\n"
+        k << EntryOpen( "PosArgs", ppt, true )
           << "        const bool full = first + " << ppt << "u <= a.count;\n"
           << "        float in[" << dim << "][" << ppt << "];\n"
           << "        float v[" << ppt << "];\n";
@@ -864,7 +911,7 @@ namespace
             if( d ) args += ", ";
             args += "a.off[" + std::to_string( d ) + "] + fn2::lane_values<F>( in[" + std::to_string( d ) + "] + p )";
         }
-        k << "            fn2::spill_lanes( " << root << "( seed, " << args << " ), v + p );\n"
+        k << "            fn2::spill_lanes( " << root << "( seed, " << args << ", tp ), v + p );\n"
           << "        }\n"
           << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
@@ -879,7 +926,7 @@ namespace
           << "            for( int p = 0; p < " << ppt << "; p++ ) if( first + p < a.count ) out[first + p] = v[p];\n"
           << "        }\n"
           << "    }\n"
-          << "    fn2::reduce_minmax( vmin, vmax, valid, mm );\n}\n";
+          << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n";
         return k.str();
     }
 }
@@ -888,11 +935,11 @@ namespace FastNoise
 {
     namespace Impl
     {
-        LoweredProgram LowerTree( const Generator* root, int entryKind, int pointsPerThread, int mathMode )
+        LoweredProgram LowerTree( const Generator* root, int entryKind, int pointsPerThread, int mathMode, bool paramMode )
         {
             LoweredProgram program;
             program.pointsPerThread = pointsPerThread;
-            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 2 && pointsPerThread != 4 && pointsPerThread != 8 ) )
+            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 4 ) )
             {
                 program.error = "invalid lowering request";
                 return program;
@@ -900,6 +947,7 @@ namespace FastNoise
 
             const int dim = EntryDims( entryKind );
             Emitter emitter;
+            emitter.paramMode = paramMode;
             std::string rootFn = emitter.Gen( root, dim );
             if( !emitter.error.empty() )
             {
@@ -928,6 +976,9 @@ namespace FastNoise
                 << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP " << ( width == 2 ? "_Pragma( \"unroll\" )" : "" ) << "\n#endif\n"
                 << "#define FN2_W " << width << "\n"
                 << "#include \"fn2_device.cuh\"\n\n"
+                << "// float node parameters: kernel arguments (one compiled kernel per tree SHAPE) -- " << emitter.params.size() << " in this tree\n"
+                << "namespace fn2 { struct TreeParams { float v[" << std::max<std::size_t>( 1, emitter.params.size() ) << "]; }; }\n"
+                << "#define FN2_TP const float* __restrict__ tp\n\n"
                 << "// value types of the node functions below: one point (float) or two points (packed FP32) per value\n"
                 << ( width == 2 ? "typedef fn2::fpair F;\ntypedef fn2::ipair I;\ntypedef fn2::bpair B;\n\n" : "typedef float F;\ntypedef fn2::i32 I;\ntypedef bool B;\n\n" )
                 << emitter.out.str();
@@ -937,6 +988,7 @@ namespace FastNoise
             else src << GridEntry( dim, rootFn, pointsPerThread );
 
             program.source = src.str();
+            program.params = std::move( emitter.params );
             return program;
         }
     }

@@ -56,6 +56,11 @@ FASTNOISE_API int fnb200Prepare( const void* node, int kind );
 /* Copies the generated CUDA source of (node, kind) into buf (NUL-terminated, truncated to bufSize); returns full length. */
 FASTNOISE_API long fnb200GetKernelSource( const void* node, int kind, char* buf, long bufSize );
 
+/* The float node parameters of the tree travel to the kernel as ONE argument (struct of floats) so that a compiled kernel serves
+ * every tree of the same shape: changing a float through any setter costs no recompile. Copies the current values for
+ * (node, kind), in the order the generated source indexes them (tp[k]), into buf (up to bufCount); returns their number. */
+FASTNOISE_API long fnb200GetKernelParams( const void* node, int kind, float* buf, long bufCount );
+
 /* Min/max accumulator helpers. The accumulator is two unsigned ints in device memory holding
  * order-preserving encodings of -min and +max; zero bytes = empty. Decode after the stream is idle. */
 FASTNOISE_API int fnb200MinMaxReset( void* deviceMinMax, void* stream );
@@ -101,6 +106,22 @@ FASTNOISE_API int fnb200SelfTestLeaf( int packed, int which, int n, int seed, fl
  * (Metadata::SerialiseNodeData): the canonical spelling of a tree. Writes a NUL-terminated string into buf
  * (truncated to bufSize) and returns its full length, 0 if the input does not decode. */
 FASTNOISE_API long fnb200CanonicalEncodedNodeTree( const char* encodedString, char* buf, long bufSize );
+
+/* ---- several GPUs, one process per GPU (the reference's model is "the caller splits one volume into calls", Generator.h:166-167)
+ * Each rank generates its slab with fnb200GenUniformGrid* (GLOBAL integer indices: bit-identical to one call over the whole grid).
+ * Two cross-rank steps exist, both NCCL collectives enqueued on a stream; NCCL is bound at run time (libnccl.so.2), no link dependency.
+ *   fnb200CommGetUniqueId  : rank 0 fills a 128-byte id; the host application broadcasts it (MPI, torch.distributed, a file ...)
+ *   fnb200CommInitRank     : every rank, with its GPU current -> communicator handle (NULL on failure)
+ *   fnb200CommAllReduceMinMax : OutputMinMax of the whole volume -- MAX over ranks of the accumulator's two unsigned keys, in place,
+ *                               on `stream`; read it afterwards with fnb200MinMaxRead. No host round trip.
+ *   fnb200CommGatherSlabs  : OPTIONAL assembly of the whole volume on every rank (only for callers that need one contiguous
+ *                            buffer): all-gather of ragged slabs, floatsPerRank[r] floats from rank r, in rank order, into
+ *                            deviceVolume. deviceSlab = NULL means "my slab already lies at its place inside deviceVolume". */
+FASTNOISE_API int fnb200CommGetUniqueId( void* uniqueId128 );
+FASTNOISE_API void* fnb200CommInitRank( int worldSize, int rank, const void* uniqueId128 );
+FASTNOISE_API int fnb200CommDestroy( void* comm );
+FASTNOISE_API int fnb200CommAllReduceMinMax( void* comm, void* deviceMinMax, void* stream );
+FASTNOISE_API int fnb200CommGatherSlabs( void* comm, const float* deviceSlab, float* deviceVolume, const long long* floatsPerRank, void* stream );
 
 /* Number of kernels this library has launched in the calling process (all threads). */
 FASTNOISE_API unsigned long long fnb200LaunchCount( void );

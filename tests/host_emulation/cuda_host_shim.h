@@ -24,6 +24,7 @@
 #define __shared__ static
 #define __restrict__ __restrict
 #define __launch_bounds__( ... )
+#define FN2_GRID_CONSTANT
 #define __align__( n ) __attribute__(( aligned( n ) ))
 
 struct Fn2HostDim { unsigned x, y, z; };

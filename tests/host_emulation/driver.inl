@@ -12,25 +12,29 @@ static fn2::FastDiv fn2_host_fast_div( unsigned d )
     return fd;
 }
 
+// The launch is smaller than the call on purpose (at most 3 blocks), so that the kernels' grid-stride loops iterate.
 template<class ARGS>
-static void fn2_host_launch( float* out, const ARGS& a, unsigned long long points, int pointsPerThread, int seed )
+static void fn2_host_launch( float* out, ARGS& a, unsigned long long points, int pointsPerThread, int seed, const float* params, int paramCount )
 {
-    const unsigned long long threads = ( points + pointsPerThread - 1 ) / pointsPerThread;
+    const unsigned long long groups = ( points + pointsPerThread - 1 ) / pointsPerThread;
+    a.groups = groups;
+    fn2::TreeParams tp {};
+    for( int i = 0; i < paramCount && i < (int)( sizeof( tp.v ) / sizeof( float ) ); i++ ) tp.v[i] = params[i];
     blockDim = { FN2_BLOCK, 1, 1 };
-    gridDim = { (unsigned)( ( threads + FN2_BLOCK - 1 ) / FN2_BLOCK ), 1, 1 };
+    gridDim = { (unsigned)std::min<unsigned long long>( 3, ( groups + FN2_BLOCK - 1 ) / FN2_BLOCK ), 1, 1 };
     for( unsigned b = 0; b < gridDim.x; b++ )
     {
         for( unsigned t = 0; t < FN2_BLOCK; t++ )
         {
             blockIdx = { b, 0, 0 };
             threadIdx = { t, 0, 0 };
-            fn2_entry( out, a, nullptr, seed );
+            fn2_entry( out, a, nullptr, seed, tp );
         }
     }
 }
 
 #if FN2_HOST_ENTRY == 0
-extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int* count, const float* step, int seed, int pointsPerThread )
+extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int* count, const float* step, int seed, int pointsPerThread, const float* params, int paramCount )
 {
     fn2::GridArgs a {};
     unsigned long long points = 1;
@@ -45,10 +49,10 @@ extern "C" void fn2_host_grid( float* out, int dims, const float* off, const int
     a.divX = fn2_host_fast_div( (unsigned)a.count[0] );
     a.divY = fn2_host_fast_div( (unsigned)a.count[1] );
     a.divZ = fn2_host_fast_div( (unsigned)a.count[2] );
-    fn2_host_launch( out, a, points, pointsPerThread, seed );
+    fn2_host_launch( out, a, points, pointsPerThread, seed, params, paramCount );
 }
 #elif FN2_HOST_ENTRY == 1
-extern "C" void fn2_host_tileable( float* out, int xSize, int ySize, float xStep, float yStep, int seed, int pointsPerThread )
+extern "C" void fn2_host_tileable( float* out, int xSize, int ySize, float xStep, float yStep, int seed, int pointsPerThread, const float* params, int paramCount )
 {
     fn2::TileArgs a {};
     const float pi2Recip = 0.15915493667f; // [Generator.inl:386-392], same float arithmetic as backend.cpp
@@ -61,11 +65,11 @@ extern "C" void fn2_host_tileable( float* out, int xSize, int ySize, float xStep
     a.ySize = ySize;
     a.total = (unsigned)( xSize * ySize );
     a.divX = fn2_host_fast_div( (unsigned)xSize );
-    fn2_host_launch( out, a, (unsigned long long)xSize * ySize, pointsPerThread, seed );
+    fn2_host_launch( out, a, (unsigned long long)xSize * ySize, pointsPerThread, seed, params, paramCount );
 }
 #else
 extern "C" void fn2_host_positions( float* out, int dims, long long count, const float* x, const float* y, const float* z, const float* w,
-                                    const float* off, int seed, int pointsPerThread )
+                                    const float* off, int seed, int pointsPerThread, const float* params, int paramCount )
 {
     fn2::PosArgs a {};
     const float* pos[4] = { x, y, z, w };
@@ -76,6 +80,6 @@ extern "C" void fn2_host_positions( float* out, int dims, long long count, const
     }
     a.count = (unsigned long long)count;
     a.vecIO = 0;
-    fn2_host_launch( out, a, (unsigned long long)count, pointsPerThread, seed );
+    fn2_host_launch( out, a, (unsigned long long)count, pointsPerThread, seed, params, paramCount );
 }
 #endif

@@ -41,7 +41,9 @@ def build_on_host(fn, text, kind, workdir, tag):
     """Lower `text` for one entry kind, compile the generated CUDA with g++ over the stand-in; returns (library, points per thread)."""
     _BUILDS[0] += 1
     tag = "%s_%d" % (tag, _BUILDS[0])  # dlopen() hands back an already loaded library for a path it has seen
-    source = fn.Generator(text).kernel_source(kind)
+    gen = fn.Generator(text)
+    source = gen.kernel_source(kind)
+    params = gen.kernel_params(kind)
     ppt = int(source.split(" point(s) per thread")[0].rsplit(" ", 1)[1])
     entry = 1 if kind == KIND_TILEABLE else (2 if kind > KIND_POS else 0)
     path = os.path.join(workdir, "tree_%s.cpp" % tag)
@@ -50,32 +52,32 @@ def build_on_host(fn, text, kind, workdir, tag):
     lib_path = os.path.join(workdir, "tree_%s.so" % tag)
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fwrapv", "-w", "-fPIC", "-shared",
                            "-I" + os.path.join(ROOT, "tests", "host_emulation"), "-I" + os.path.join(ROOT, "fastnoise2_b200", "csrc", "device"), path, "-o", lib_path])
-    return ctypes.CDLL(lib_path), ppt
+    return ctypes.CDLL(lib_path), (ppt, params)
 
 
 def run_on_host(fn, text, dims, seed, workdir, tag):
     """dims-D uniform grid of GRIDS[dims] through the generated entry kernel, on the host."""
-    lib, ppt = build_on_host(fn, text, dims, workdir, tag)
+    lib, (ppt, params) = build_on_host(fn, text, dims, workdir, tag)
     g = GRIDS[dims]
     out = np.zeros(int(np.prod(g["n"])), np.float32)
     lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), dims, (ctypes.c_float * dims)(*g["off"]), (ctypes.c_int * dims)(*g["n"]),
-                      (ctypes.c_float * dims)(*g["step"]), seed, ppt)
+                      (ctypes.c_float * dims)(*g["step"]), seed, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
     return out
 
 
 def run_tileable_on_host(fn, text, nx, ny, sx, sy, seed, workdir, tag):
-    lib, ppt = build_on_host(fn, text, KIND_TILEABLE, workdir, tag)
+    lib, (ppt, params) = build_on_host(fn, text, KIND_TILEABLE, workdir, tag)
     out = np.zeros(nx * ny, np.float32)
-    lib.fn2_host_tileable(out.ctypes.data_as(ctypes.c_void_p), nx, ny, ctypes.c_float(sx), ctypes.c_float(sy), seed, ppt)
+    lib.fn2_host_tileable(out.ctypes.data_as(ctypes.c_void_p), nx, ny, ctypes.c_float(sx), ctypes.c_float(sy), seed, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
     return out
 
 
 def run_positions_on_host(fn, text, pos, offsets, seed, workdir, tag):
     dims = len(pos)
-    lib, ppt = build_on_host(fn, text, KIND_POS + dims, workdir, tag)
+    lib, (ppt, params) = build_on_host(fn, text, KIND_POS + dims, workdir, tag)
     out = np.zeros(len(pos[0]), np.float32)
     ptrs = [p.ctypes.data_as(ctypes.c_void_p) for p in pos] + [None] * (4 - dims)
-    lib.fn2_host_positions(out.ctypes.data_as(ctypes.c_void_p), dims, ctypes.c_longlong(len(pos[0])), *ptrs, (ctypes.c_float * dims)(*offsets), seed, ppt)
+    lib.fn2_host_positions(out.ctypes.data_as(ctypes.c_void_p), dims, ctypes.c_longlong(len(pos[0])), *ptrs, (ctypes.c_float * dims)(*offsets), seed, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
     return out
 
 
@@ -198,10 +200,10 @@ def setter_fuzz(fn, ref_lib, count, seed, workdir):
         holder = type("OneTree", (), {"Generator": staticmethod(lambda text, g=tree.ours[0]: g)})
         for dims in (2, 3):
             g = GRIDS[dims]
-            lib, ppt = build_on_host(holder, "", dims, workdir, "setters")
+            lib, (ppt, params) = build_on_host(holder, "", dims, workdir, "setters")
             got = np.zeros(int(np.prod(g["n"])), np.float32)
             lib.fn2_host_grid(got.ctypes.data_as(ctypes.c_void_p), dims, (ctypes.c_float * dims)(*g["off"]), (ctypes.c_int * dims)(*g["n"]),
-                              (ctypes.c_float * dims)(*g["step"]), index, ppt)
+                              (ctypes.c_float * dims)(*g["step"]), index, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
             want, mm = np.empty_like(got), np.zeros(2, np.float32)
             call = ref_lib.fnGenUniformGrid2D if dims == 2 else ref_lib.fnGenUniformGrid3D
             call(tree.theirs[0], want.ctypes.data, *g["off"], *g["n"], *g["step"], index, mm.ctypes.data)
@@ -309,17 +311,18 @@ if __name__ == "__main__":
 
 
 def test_smaller_points_per_thread_variants_on_host(fn, ref, tmp_path, monkeypatch):
-    """The 1- and 2-points-per-thread variants (what the library launches for row widths that 4 does not divide, and for
-    calls too small to fill the GPU) on odd grid sizes."""
+    """The 1-point-per-thread variant (what the library launches for row widths that 4 does not divide, and for calls too small
+    to fill the GPU) on odd grid sizes, and the literal-parameter form of the kernels (FASTNOISE2_B200_LITERALS=1)."""
     failures = []
-    for ppt, n in (("1", (9, 7, 5)), ("2", (10, 7, 3))):
+    for ppt, literals, n in (("1", "0", (9, 7, 5)), ("1", "1", (10, 7, 3)), ("4", "1", (12, 7, 3))):
         monkeypatch.setenv("FASTNOISE2_B200_PPT", ppt)
+        monkeypatch.setenv("FASTNOISE2_B200_LITERALS", literals)
         for name in ("c4_terrain", "c3a_cellular_distance"):
-            lib, got_ppt = build_on_host(fn, fn.TREES[name], 3, str(tmp_path), "ppt")
-            assert got_ppt == int(ppt)
+            lib, (got_ppt, params) = build_on_host(fn, fn.TREES[name], 3, str(tmp_path), "ppt")
+            assert got_ppt == int(ppt) and (len(params) > 1) == (literals == "0")
             out = np.zeros(int(np.prod(n)), np.float32)
             lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), 3, (ctypes.c_float * 3)(0.5, -2.0, 3.0), (ctypes.c_int * 3)(*n),
-                              (ctypes.c_float * 3)(1.3, 1.1, 0.9), 7, got_ppt)
+                              (ctypes.c_float * 3)(1.3, 1.1, 0.9), 7, got_ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
             want = helpers.RefNode(ref, fn.TREES[name]).grid3d(0.5, -2.0, 3.0, *n, 1.3, 1.1, 0.9, 7)[0]
             if not same(out, want):
                 failures.append((ppt, name, helpers.compare(out, want)))

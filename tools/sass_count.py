@@ -45,10 +45,13 @@ def main():
     fn.set_math_mode(args.math)
     text = fn.TREES.get(args.tree, args.tree)
     g = fn.Generator(text)
-    g.prepare(args.kind)
-    cubins = glob.glob(os.path.join(cache, "*.cubin"))
+    g.prepare(args.kind)  # compiles the 4- and the 1-point-per-thread variant (only the latter with --ppt 1)
+    cubins = sorted(glob.glob(os.path.join(cache, "*.cubin")), key=os.path.getmtime)
     assert cubins, fn.last_error()
-    for cubin in cubins:
+    for cubin, ppt in zip(cubins, [4, 1] if len(cubins) == 2 else [args.ppt or 4]):
+        open(cubin + ".txt", "w").write("%d point(s) per thread" % ppt)
+        if args.ppt and ppt != args.ppt:
+            continue
         report(cubin, args)
         if args.keep:
             subprocess.check_call(["cp", cubin, args.keep])
@@ -69,12 +72,29 @@ def report(cubin, args):
             continue
         ops[op] += 1
         n += 1
-    back = len(re.findall(r"BRA\s+`\(\.L_x_\d+\)", sass))
-    print("%s: regs %s, %d instructions (%.1f KB), %d BRA" % (os.path.basename(cubin), regs.group(1) if regs else "?", n, n * 16 / 1024.0, back))
-    ppt = args.ppt or 4
-    for op, c in ops.most_common(args.top):
+    ppt = int(re.search(r"(\d+) point\(s\) per thread", open(cubin + ".txt").read()).group(1)) if os.path.exists(cubin + ".txt") else (args.ppt or 4)
+    # the persistent grid-stride loop: the LAST backward branch of fn2_entry; with the octave loops unrolled its body is what a
+    # thread executes per group of `ppt` points (divide slow paths, which are CALLed, are outside and almost never run)
+    rows = []
+    for line in sass.split("\n"):
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*)", line)
+        if m and m.group(2).split(".")[0] != "NOP":
+            rows.append((int(m.group(1), 16), m.group(2).split(".")[0], m.group(3)))
+    loops = []
+    for addr, op, rest in rows:
+        t = re.search(r"BRA(?:\.U)?\s.*?(0x[0-9a-f]+)", op + rest)
+        if op == "BRA" and t and int(t.group(1), 16) < addr:
+            loops.append((int(t.group(1), 16), addr))
+    print("%s: ppt %d, regs %s, %d instructions (%.1f KB), %d backward branches" % (os.path.basename(cubin), ppt, regs.group(1) if regs else "?", n, n * 16 / 1024.0, len(loops)))
+    body = ops
+    if loops:
+        lo, hi = min(l[0] for l in loops), max(l[1] for l in loops)
+        body = collections.Counter(op for addr, op, _ in rows if lo <= addr <= hi)
+        nb = sum(body.values())
+        print("  outermost loop body: %d instructions = %.1f per point; outside the loop: %d" % (nb, nb / ppt, n - nb))
+    for op, c in body.most_common(args.top):
         print("  %-10s %6d  %7.1f /pt" % (op, c, c / ppt))
-    print("  %-10s %6d  %7.1f /pt" % ("total", n, n / ppt))
+    print("  %-10s %6d  %7.1f /pt" % ("total", sum(body.values()), sum(body.values()) / ppt))
 
 
 if __name__ == "__main__":
