@@ -71,6 +71,7 @@ PROTOTYPES = {
     "fnb200GetKernelParams": (ctypes.c_long, [P, I, P, ctypes.c_long]),
     "fnb200SelfTestInvSqrt": (LL, [F, F]),
     "fnb200SelfTestLeaf": (I, [I, I, I, I, F, P]),
+    "fnb200DebugIntermediates": (I, [I, I, F, F, I, I, I, F, F, F, F, P]),
     "fnb200MinMaxReset": (I, [P, P]),
     "fnb200MinMaxRead": (I, [P, P, P]),
     "fnb200GenUniformGrid2D": (I, [P, P, F, F, I, I, F, F, I, I, I, P, P]),

@@ -42,6 +42,7 @@ using namespace FastNoise::Impl;
 namespace
 {
     constexpr int kBlock = 256;
+    constexpr int kItersPerThread = 8; // groups one thread walks in a large call (see Launch)
 
     thread_local std::string tLastError;
     std::atomic<int> gMathMode { 0 };
@@ -679,9 +680,14 @@ namespace FastNoise
         {
             unsigned long long blocks = ( groups + kBlock - 1 ) / kBlock;
             if( blocks == 0 ) return true;
-            // persistent: no more blocks than the device keeps resident; the kernel's grid-stride loop covers the rest
-            const unsigned long long resident = (unsigned long long)std::max( 1, m->residentBlocks ) * (unsigned)std::max( 1, EnvInt( "FASTNOISE2_B200_WAVES", 1 ) );
-            if( EnvInt( "FASTNOISE2_B200_PERSISTENT", 1 ) != 0 ) blocks = std::min( blocks, resident );
+            // Grid-stride launch: every thread walks about kItersPerThread groups, so the per-block work (table staging, the min/max
+            // reduction) is paid once per that many groups, while the grid stays many waves deep -- the hardware block scheduler
+            // keeps balancing the SMs to the end of the call. (A grid of exactly the resident blocks, every thread walking the whole
+            // call, measured 11 % SLOWER on the heavy trees: warps that the issue arbiter favours finish early and the tail runs
+            // under-occupied. profiles/r2_perf_sweep.txt) Never fewer blocks than the device keeps resident.
+            const unsigned long long resident = (unsigned long long)std::max( 1, m->residentBlocks );
+            const int iters = EnvInt( "FASTNOISE2_B200_ITERS", kItersPerThread );
+            blocks = iters <= 0 ? std::min( blocks, resident ) : std::min( blocks, std::max( resident, ( blocks + iters - 1 ) / iters ) );
             if( blocks > 0x7fffffffull )
             {
                 SetLastError( "launch too large" );

@@ -53,6 +53,7 @@ namespace FastNoise
         const std::string& LastError();
         long long SelfTestInvSqrt( float lo, float hi ); // device_check.cu
         int SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut ); // device_check.cu
+        int DebugIntermediates( int mode, int seed, float frequency, float jitter, int nx, int ny, int nz, float ox, float oy, float oz, float step, int* hostOut ); // device_check.cu
         int MathMode();
         void SetMathMode( int mode );
         unsigned long long LaunchCount();

@@ -385,5 +385,9 @@ extern "C"
 
     double fnb200MeasureAluPeak( int mode, int iters ) { return Impl::MeasureAluPeak( mode, iters ); }
     long long fnb200SelfTestInvSqrt( float lo, float hi ) { return Impl::SelfTestInvSqrt( lo, hi ); }
+    int fnb200DebugIntermediates( int mode, int seed, float frequency, float jitter, int xCount, int yCount, int zCount, float xOffset, float yOffset, float zOffset, float step, int* hostOut )
+    {
+        return Impl::DebugIntermediates( mode, seed, frequency, jitter, xCount, yCount, zCount, xOffset, yOffset, zOffset, step, hostOut );
+    }
     int fnb200SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut ) { return Impl::SelfTestLeaf( packed, which, n, seed, step, hostOut ); }
 }

@@ -415,7 +415,7 @@ namespace fn2
     }
 
     template<int DF, bool SIZEJ, class PF, class F>
-    FN2_DI void cellular_lookup3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP, F& cellX, F& cellY, F& cellZ )
+    FN2_DI void cellular_lookup3( i32 seed, F x, F y, F z, F jitter, F sizeJitter, PF minkowskiP, F& cellX, F& cellY, F& cellZ, typename pack<F>::I* dbg = nullptr )
     {
         typedef typename pack<F>::I I;
         typedef typename pack<F>::B B;
@@ -427,6 +427,11 @@ namespace fn2
         xc = imul( xc, kPX );
         ycBase = imul( ycBase, kPY );
         zcBase = imul( zcBase, kPZ );
+        if( dbg ) // integer intermediates for the parity tests (fnb200DebugIntermediates): primed base cell, then the closest cell's hash
+        {
+            dbg[0] = xc; dbg[1] = ycBase; dbg[2] = zcBase;
+            dbg[3] = 0;
+        }
 
         for( int xi = 0; xi < 3; xi++ )
         {
@@ -454,6 +459,7 @@ namespace fn2
                     cellX = select( closer, localX, cellX );
                     cellY = select( closer, localY, cellY );
                     cellZ = select( closer, localZ, cellZ );
+                    if( dbg ) dbg[3] = select( closer, hash, dbg[3] );
                     zcf += 1.0f;
                     zc = iadd( zc, kPZ );
                 }

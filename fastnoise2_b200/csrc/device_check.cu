@@ -117,10 +117,57 @@ extern "C" __global__ void __launch_bounds__( 256 ) fn2_selftest_inv_sqrt( unsig
     if( bad ) atomicAdd( mismatches, bad );
 }
 
+// Integer intermediates of the lattice / cell search on a 3D uniform grid, 8 ints per point, through the SAME device functions the
+// generated kernels call (their optional debug sink). mode 0: Simplex -- primed base-cell coordinates [Simplex.inl:76-80], HashPrimesHB
+// [Utils.inl:232-240] of the four vertices, and the scaled product the gradient lookup consumes. mode 1: Cellular -- primed base cell
+// [Cellular.inl:379-384 / 586-592] and HashPrimesHB of the closest cell (the CellularLookup winner [Cellular.inl:612-626]).
+// Positions as the batch driver makes them: fma( float(index), step, offset ) * frequency.
+extern "C" __global__ void __launch_bounds__( 256 ) fn2_debug_intermediates( int* __restrict__ out, int mode, int seed, float frequency, float jitter,
+                                                                              int nx, int ny, int nz, float ox, float oy, float oz, float step )
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    fn2::stage_tables();
+    if( i >= (long long)nx * ny * nz ) return;
+    const int ix = (int)( i % nx ), iy = (int)( ( i / nx ) % ny ), iz = (int)( i / ( (long long)nx * ny ) );
+    float x = fn2::fma_( fn2::cvt_f( ix ), step, ox ), y = fn2::fma_( fn2::cvt_f( iy ), step, oy ), z = fn2::fma_( fn2::cvt_f( iz ), step, oz );
+    x *= frequency;
+    y *= frequency;
+    z *= frequency;
+    int dbg[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    float sink;
+    if( mode == 0 )
+    {
+        sink = fn2::simplex3( seed, x, y, z, dbg );
+    }
+    else
+    {
+        float cx, cy, cz;
+        fn2::cellular_lookup3<1, false>( seed, x, y, z, fn2::kJitter3D * jitter, 0.0f, ConstP { 0.0f }, cx, cy, cz, dbg );
+        sink = cx + cy + cz;
+        dbg[4] = __float_as_int( cx );
+        dbg[5] = __float_as_int( cy );
+        dbg[6] = __float_as_int( cz );
+    }
+    if( sink == 12345.678f ) dbg[7] ^= 1; // keeps the float path alive
+    for( int k = 0; k < 8; k++ ) out[i * 8 + k] = dbg[k];
+}
+
 namespace FastNoise
 {
     namespace Impl
     {
+        int DebugIntermediates( int mode, int seed, float frequency, float jitter, int nx, int ny, int nz, float ox, float oy, float oz, float step, int* hostOut )
+        {
+            const long long n = (long long)nx * ny * nz;
+            if( n <= 0 || n > ( 1ll << 28 ) || !hostOut || ( mode != 0 && mode != 1 ) ) return -1;
+            int* dev = nullptr;
+            if( cudaMalloc( &dev, (size_t)n * 8 * sizeof( int ) ) != cudaSuccess ) return -2;
+            fn2_debug_intermediates<<<(unsigned)( ( n + 255 ) / 256 ), 256>>>( dev, mode, seed, frequency, jitter, nx, ny, nz, ox, oy, oz, step );
+            const cudaError_t e = cudaMemcpy( hostOut, dev, (size_t)n * 8 * sizeof( int ), cudaMemcpyDeviceToHost );
+            cudaFree( dev );
+            return e == cudaSuccess ? 0 : -3;
+        }
+
         // Runs leaf `which` of the device library over n points (one point per value, or two with packed FP32) into hostOut.
         int SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut )
         {

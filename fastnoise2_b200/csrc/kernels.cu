@@ -61,14 +61,32 @@ namespace
                         f[k] = fmaf( f[k], a, b );
                         u[k] = ( u[k] ^ m ) & ( u[( k + 1 ) & 7] | 0x55555555u );
                     }
-                    if( MODE >= 4 && ( k & 1 ) == 0 )                                 // packed FP32: one FFMA2 per pair of chains
+                    if( MODE >= 4 && MODE <= 8 && ( k & 1 ) == 0 )                    // packed FP32: one FFMA2 per pair of chains
                     {
-                        const float2 r = __ffma2_rn( make_float2( f[k], f[k + 1] ), make_float2( a, a ), make_float2( b, b ) );
+                        const float2 r = MODE == 8 ? __ffma2_rn( make_float2( f[k], f[k + 1] ), make_float2( 1.0001f, 1.0001f ), make_float2( 0.5f, 0.5f ) )
+                                                   : __ffma2_rn( make_float2( f[k], f[k + 1] ), make_float2( a, a ), make_float2( b, b ) );
                         f[k] = r.x;
                         f[k + 1] = r.y;
                     }
                     if( MODE == 5 && ( k & 1 ) == 0 ) u[k] = ( u[k] ^ m ) & ( u[( k + 2 ) & 7] | 0x55555555u );   // + 1 LOP3 per FFMA2
                     if( MODE == 6 ) u[k] = ( u[k] ^ m ) & ( u[( k + 1 ) & 7] | 0x55555555u );                     // + 2 LOP3 per FFMA2
+                    // The question behind the axis-packed leaves: does an FFMA2 take ONE issue slot? 1 FFMA2 + 1 LOP3 per pair of chains
+                    // needs 2 cycles of the FMA pipe, 2 of the ALU pipe and 2 issue slots if it does (3 if the FFMA2 takes two);
+                    // mode 9 is the scalar counterpart (2 FFMA + 1 LOP3: 3 issue slots), mode 8 the FFMA2 with a broadcast operand.
+                    if( MODE == 7 && ( k & 1 ) == 0 ) u[k] = ( u[k] ^ m ) & u[( k + 2 ) & 7];                     // 1 FFMA2 + 1 LOP3 (one instruction)
+                    if( MODE == 8 && ( k & 1 ) == 0 ) u[k] = ( u[k] ^ m ) & u[( k + 2 ) & 7];
+                    if( MODE == 10 && ( k & 1 ) == 0 )                                                            // FFMA2 with three register-PAIR operands + 1 LOP3
+                    {
+                        const float2 r = __ffma2_rn( make_float2( f[k], f[k + 1] ), make_float2( f[( k + 2 ) & 7], f[( k + 3 ) & 7] ), make_float2( f[( k + 4 ) & 7], f[( k + 5 ) & 7] ) );
+                        f[k] = r.x;
+                        f[k + 1] = r.y;
+                        u[k] = ( u[k] ^ m ) & u[( k + 2 ) & 7];
+                    }
+                    if( MODE == 9 )
+                    {
+                        f[k] = fmaf( f[k], a, b );
+                        if( ( k & 1 ) == 0 ) u[k] = ( u[k] ^ m ) & u[( k + 2 ) & 7];
+                    }
                 }
             }
         }
@@ -113,7 +131,11 @@ namespace FastNoise
                 case 3: AluProbeKernel<3><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 case 4: AluProbeKernel<4><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 case 5: AluProbeKernel<5><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
-                default: AluProbeKernel<6><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 6: AluProbeKernel<6><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 7: AluProbeKernel<7><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 8: AluProbeKernel<8><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                case 9: AluProbeKernel<9><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
+                default: AluProbeKernel<10><<<blocks, 256>>>( sink, n, 1.0001f, 0.5f, 0x2545F491u ); break;
                 }
             };
             launch( 16 ); // warm-up
@@ -127,7 +149,8 @@ namespace FastNoise
                 cudaEventSynchronize( t1 );
                 float ms = 0;
                 cudaEventElapsedTime( &ms, t0, t1 );
-                const double perRep = mode == 3 ? 16 : ( mode == 5 ? 12 : ( mode == 6 ? 16 : 8 ) ); // lane-operations per repetition (an FFMA2 counts as 2)
+                // lane-operations per repetition (an FFMA2 counts as 2); modes 7-9: 8 FP lane-ops + 4 LOP3
+                const double perRep = mode == 3 ? 16 : ( mode == 5 ? 12 : ( mode == 6 ? 16 : ( mode >= 7 ? 12 : 8 ) ) );
                 const double opsPerThread = (double)iters * 16 * perRep;
                 const double rate = opsPerThread * blocks * 256 / ( ms * 1e-3 );
                 if( ms > 0 && rate > best ) best = rate;

@@ -102,6 +102,14 @@ FASTNOISE_API long long fnb200SelfTestInvSqrt( float lo, float hi );
  * point per value (packed = 0) or two points per value with packed FP32 instructions (packed = 1). The two must agree bit for bit. */
 FASTNOISE_API int fnb200SelfTestLeaf( int packed, int which, int n, int seed, float step, float* hostOut );
 
+/* Debug: the INTEGER intermediates of the lattice / cell search for a 3D uniform grid (positions fma( float(i), step, offset ) * frequency),
+ * 8 ints per point into hostOut, written by the same device functions the generated kernels call:
+ *   mode 0 (Simplex)  : primed base-cell coordinates x, y, z; HashPrimesHB of the 4 simplex vertices; [7] = vertex 0's product as the gradient lookup sees it
+ *   mode 1 (Cellular) : primed base-cell coordinates x, y, z; HashPrimesHB of the closest cell; bit patterns of that cell's point x, y, z; 0
+ * `jitter` is the Cellular jitter modifier (1 = default). The parity tests compare these with the oracle's (fn2oDebugGrid3D). */
+FASTNOISE_API int fnb200DebugIntermediates( int mode, int seed, float frequency, float jitter, int xCount, int yCount, int zCount,
+                                            float xOffset, float yOffset, float zOffset, float step, int* hostOut );
+
 /* Decodes `encodedString` into NodeData records (Metadata::DeserialiseNodeData) and serialises them again
  * (Metadata::SerialiseNodeData): the canonical spelling of a tree. Writes a NUL-terminated string into buf
  * (truncated to bufSize) and returns its full length, 0 if the input does not decode. */

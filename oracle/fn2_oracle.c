@@ -555,6 +555,11 @@ static float pow4( float v ) { v *= v; v *= v; return v; }
  * them in the reference's order (hash of the lattice point, offset to it, falloff^4) and each consumer folds them its way. */
 typedef struct { i32 hash; float d[4]; float falloff; } Vert;
 
+/* Debug sink (fn2oDebugGrid3D): when set, the 3D Simplex lattice and the CellularLookup search write their INTEGER intermediates
+ * here, 8 ints per point -- primed base-cell coordinates, HashPrimesHB [Utils.inl:232-240] of the simplex vertices / of the closest
+ * cell -- so the tests can compare them with the GPU's (fnb200DebugIntermediates) directly instead of inferring them from floats. */
+static i32* gDebug = 0;
+
 static int simplex_vertices( i32 seed, int dim, const float* p, Vert* out )
 {
     if( dim == 2 ) /* Simplex.inl:7-56 */
@@ -596,6 +601,11 @@ static int simplex_vertices( i32 seed, int dim, const float* p, Vert* out )
         i32 Q3[3] = { iadd( P[0], kPrime[0] ), iadd( P[1], kPrime[1] ), iadd( P[2], kPrime[2] ) };
         const i32* Q[4] = { P, Q1, Q2, Q3 };
         float dd[4][3] = { { dx0, dy0, dz0 }, { dx1, dy1, dz1 }, { dx2, dy2, dz2 }, { dx3, dy3, dz3 } }, ff[4] = { f0, f1, f2, f3 };
+        if( gDebug )
+        {
+            for( int k = 0; k < 3; k++ ) gDebug[k] = P[k];
+            for( int v = 0; v < 4; v++ ) gDebug[3 + v] = hash_hb( seed, Q[v], 3 );
+        }
         for( int v = 0; v < 4; v++ )
         {
             out[v].hash = hash_primes( seed, Q[v], 3 );
@@ -1022,6 +1032,11 @@ static float cellular( const Node* n, int mode, i32 seed, int dim, const float* 
     i32 c0[4]; float cf0[4];
     for( int d = 0; d < dim; d++ ) { c0[d] = iadd( cvt_i( p[d] ), -1 ); cf0[d] = (float)c0[d]; }
 
+    if( gDebug && dim == 3 && mode == 2 )
+    {
+        for( int d = 0; d < 3; d++ ) gDebug[d] = imul( c0[d], kPrime[d] );
+        gDebug[3] = 0;
+    }
     int total = dim == 2 ? 9 : ( dim == 3 ? 27 : 81 );
     for( int it = 0; it < total; it++ )
     {
@@ -1080,6 +1095,7 @@ static float cellular( const Node* n, int mode, i32 seed, int dim, const float* 
             int closer = nd < best;
             best = fmin_x86( nd, best );
             if( closer ) for( int d = 0; d < dim; d++ ) cell[d] = local[d];
+            if( closer && gDebug && dim == 3 ) { gDebug[3] = hash; for( int d = 0; d < 3; d++ ) gDebug[4 + d] = f2b( local[d] ); }
         }
     }
 
@@ -1467,6 +1483,23 @@ void fn2oGrid( const void* node, float* out, int dims, const float* off, const i
         }
     }
     if( minmax ) { minmax[0] = mm.mn; minmax[1] = mm.mx; }
+}
+
+/* Integer intermediates of a 3D uniform grid, 8 ints per point (see gDebug): the tree is evaluated point by point with the sink set.
+ * Meant for trees whose root is Simplex or CellularLookup; not thread-safe. */
+void fn2oDebugGrid3D( const void* node, int* out8, const float* off, const int* n, const float* step, int seed )
+{
+    size_t i = 0;
+    for( int z = 0; z < n[2]; z++ )
+        for( int y = 0; y < n[1]; y++ )
+            for( int x = 0; x < n[0]; x++, i++ )
+            {
+                float p[3] = { fmaf( (float)x, step[0], off[0] ), fmaf( (float)y, step[1], off[1] ), fmaf( (float)z, step[2], off[2] ) };
+                for( int k = 0; k < 8; k++ ) out8[i * 8 + k] = 0;
+                gDebug = out8 + i * 8;
+                (void)eval( (const Node*)node, seed, 3, p );
+                gDebug = 0;
+            }
 }
 
 /* GenTileable2D [Generator.inl:370-433], rows [rowBegin, rowBegin + rowCount) */

@@ -162,6 +162,8 @@ def load_port():
     lib.fn2oGrid.argtypes = [P, P, I, P, P, P, I, LL, LL, P]
     lib.fn2oTileable.argtypes = [P, P, I, I, F, F, I, I, I, P]
     lib.fn2oPositions.argtypes = [P, P, I, LL, P, P, P, P, P, I, P]
+    if hasattr(lib, "fn2oDebugGrid3D"):
+        lib.fn2oDebugGrid3D.argtypes = [P, P, P, P, P, I]
     return lib
 
 

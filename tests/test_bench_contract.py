@@ -46,3 +46,28 @@ def test_node_benchmark_reference_arm_runs():
     lines = [line for line in out.stdout.splitlines() if line.strip()]
     assert len(lines) == 2 and lines[0].startswith("2D/") and lines[1].startswith("3D/")
     assert all("/Coherent Noise/Perlin" in line and "M items/s" in line for line in lines)
+
+
+def test_node_benchmark_reference_arm_has_the_node_trees_group():
+    """The "Node Trees" group of the reference harness (FastNoiseBenchmark.cpp:152-166): both demo trees, every dimensionality."""
+    if helpers.load_ref("relaxed_avx2") is None and helpers.load_ref("relaxed_avx512") is None:
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "node_benchmark.py"), "--impl", "reference", "--filter", "node trees", "--dims", "2", "3", "4",
+                          "--positions", "1024", "--iterations", "2", "--cpu-seconds", "0.05"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.strip()]
+    assert len(lines) == 6 and all("/Node Trees/" in line for line in lines)
+    assert [("Mountain Terrain" in line) for line in lines] == [True] * 3 + [False] * 3
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the `config` of the two arms' lines: it comes from one function, fed the same arguments."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    for workload, world, scaling in (("c4", 1, "strong"), ("c4", 8, "strong"), ("c5", 2, "weak")):
+        args = argparse.Namespace(workload=workload, scaling=scaling)
+        a = bench.config_of(args, bench.WORKLOADS[workload], world)
+        b = bench.config_of(argparse.Namespace(workload=workload, scaling=scaling), bench.WORKLOADS[workload], world)
+        assert a == b and a["encoded_tree"] and a["points"] > 0 and "exceeds L2" in a["l2"]
+    assert bench.slab_range(1024, 7, 8) == (896, 1024) and bench.slab_range(10, 0, 3) == (0, 4)

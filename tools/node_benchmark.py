@@ -48,6 +48,33 @@ def build_generator(lib, node_id, handles):
     return generator
 
 
+# the "Node Trees" group of the reference harness (FastNoiseBenchmark.cpp:152-166): the two trees shipped with its Node Editor
+# (tools/NodeEditor/util/DemoNodeTrees.inl:5-6, written by the reference's own encoder)
+NODE_TREES = [
+    ("Mountain Terrain", "E@BBZEG@BD8JFgIECArXIzwECiQIw/UoPwkuAAE@BJDQAH@BC@AIEAJBw@ABZEED0KV78YZmZmPwQDmpkZPwsAAIA/HAMAAHBCBA=="),
+    ("Cellular Caves", "FgIcCS4AAQ@BklCQs@BlRBDNzMw9G@AIMAgAw@ADgC@BCiQIzczMPgkJ@BPkIQH4XrPhjNzEw/DBIkCM3MzD4JCQ@ADBCCAE@BQzczMvhg@B/JAL/BAAL7FE4PgQKFwkNCQg@CQQQDuB4FPwt7FC4/BAOPwnU8DA=="),
+]
+
+
+def subjects(lib, name_filter):
+    """(group, name, builder) for every node type, then the Node Trees group -- the registration order of the reference harness."""
+    for node_id in range(lib.fnGetMetadataCount()):
+        name = lib.fnGetMetadataName(node_id).decode()
+        if name_filter and name_filter.lower() not in name.lower():
+            continue
+        yield group_name(lib, node_id), name, (lambda handles, i=node_id: build_generator(lib, i, handles))
+    for name, text in NODE_TREES:
+        if name_filter and name_filter.lower() not in name.lower() and name_filter.lower() != "node trees":
+            continue
+
+        def decode(handles, text=text):
+            h = lib.fnNewFromEncodedNodeTree(text.encode(), 0xFFFFFFFF)
+            if h:
+                handles.append(h)
+            return h or None
+        yield "Node Trees", name, decode
+
+
 def group_name(lib, node_id):
     count = lib.fnGetMetadataGroupCount(node_id)
     return lib.fnGetMetadataGroupName(node_id, count - 1).decode() if count else "Misc"
@@ -67,14 +94,11 @@ def bench_product(args):
     stream.synchronize()
     sp = ctypes.c_void_p(stream.cuda_stream)
     rows = []
-    for node_id in range(lib.fnGetMetadataCount()):
-        name = lib.fnGetMetadataName(node_id).decode()
-        if args.filter and args.filter.lower() not in name.lower():
-            continue
+    for group, name, build in subjects(lib, args.filter):
         handles = []
-        gen = build_generator(lib, node_id, handles)
+        gen = build(handles)
         for dim in args.dims:
-            label = "%dD/B200_SM100A/%s/%s" % (dim, group_name(lib, node_id), name)
+            label = "%dD/B200_SM100A/%s/%s" % (dim, group, name)
             if gen is None:
                 rows.append({"name": label, "error": "could not set valid sources"})
                 continue
@@ -118,14 +142,11 @@ def bench_reference(args):
     out = np.empty(n, np.float32)
     p = pos.ctypes.data
     rows = []
-    for node_id in range(lib.fnGetMetadataCount()):
-        name = lib.fnGetMetadataName(node_id).decode()
-        if args.filter and args.filter.lower() not in name.lower():
-            continue
+    for group, name, build in subjects(lib, args.filter):
         handles = []
-        gen = build_generator(lib, node_id, handles)
+        gen = build(handles)
         for dim in args.dims:
-            label = "%dD/%s/%s/%s" % (dim, variant, group_name(lib, node_id), name)
+            label = "%dD/%s/%s/%s" % (dim, variant, group, name)
             if gen is None:
                 rows.append({"name": label, "error": "could not set valid sources"})
                 continue
