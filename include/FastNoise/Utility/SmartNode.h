@@ -73,7 +73,7 @@ namespace FastNoise
 
         SmartNode( const SmartNode& other ) noexcept : mNode( other.mNode ) { Acquire( mNode ); }
 
-        template<typename U, typename = std::enable_if_t<std::is_convertible<U*, T*>::value>>
+        template<typename U, typename = typename std::enable_if<std::is_convertible<U*, T*>::value>::type>
         SmartNode( const SmartNode<U>& other ) noexcept : mNode( other.mNode ) { Acquire( mNode ); }
 
         /// aliasing form: share ownership with `owner` but point at `node` (already cast by the caller)
@@ -82,7 +82,7 @@ namespace FastNoise
 
         SmartNode( SmartNode&& other ) noexcept : mNode( other.mNode ) { other.mNode = nullptr; }
 
-        template<typename U, typename = std::enable_if_t<std::is_convertible<U*, T*>::value>>
+        template<typename U, typename = typename std::enable_if<std::is_convertible<U*, T*>::value>::type>
         SmartNode( SmartNode<U>&& other ) noexcept : mNode( other.mNode ) { other.mNode = nullptr; }
 
         ~SmartNode() { Drop(); }
@@ -94,7 +94,7 @@ namespace FastNoise
             return *this;
         }
 
-        template<typename U, typename = std::enable_if_t<std::is_convertible<U*, T*>::value>>
+        template<typename U, typename = typename std::enable_if<std::is_convertible<U*, T*>::value>::type>
         SmartNode& operator=( const SmartNode<U>& other ) noexcept
         {
             SmartNode copy( other );
@@ -108,7 +108,7 @@ namespace FastNoise
             return *this;
         }
 
-        template<typename U, typename = std::enable_if_t<std::is_convertible<U*, T*>::value>>
+        template<typename U, typename = typename std::enable_if<std::is_convertible<U*, T*>::value>::type>
         SmartNode& operator=( SmartNode<U>&& other ) noexcept
         {
             SmartNode moved( std::move( other ) );

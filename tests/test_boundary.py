@@ -267,10 +267,11 @@ def test_cpp_api_surface_compiles_and_behaves(fn, tmp_path):
 
 
 def test_public_headers_parse_as_cpp11(tmp_path):
-    """The reference keeps its public headers C++11-clean (tests/FastNoiseCpp11Include.cpp); C++14 is what these need."""
+    """The reference keeps its public headers C++11-clean (tests/FastNoiseCpp11Include.cpp); so do these, a typed New<T>() included."""
     src = tmp_path / "inc.cpp"
-    src.write_text("#include <FastNoise/FastNoise.h>\n#include <FastNoise/Metadata.h>\n#include <FastNoise/FastNoise_C.h>\nint main() { return 0; }\n")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)])
+    src.write_text("#include <FastNoise/FastNoise.h>\n#include <FastNoise/Metadata.h>\n#include <FastNoise/FastNoise_C.h>\n#include <FastNoise/FastNoise_B200.h>\n"
+                   "int main() { auto n = FastNoise::New<FastNoise::FractalFBm>(); n->SetSource( FastNoise::New<FastNoise::Simplex>() ); return n ? 0 : 1; }\n")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)])
 
 
 def test_canonical_reencoding_preserves_random_trees(fn, ref):
@@ -516,3 +517,39 @@ def test_reflection_getters_match_live_reference_including_invalid_arguments(fn,
     assert a.fnGetMetadataID(ha) == b.fnGetMetadataID(hb) == 13
     for lib, h in ((a, ha), (a, ca), (b, hb), (b, cb)):
         lib.fnDeleteNodeRef(h)
+
+
+def test_float_parameters_are_kernel_arguments_not_source_text(fn):
+    """One compiled kernel serves every tree of the same SHAPE: a float edit through any setter (the reference applies it at once,
+    FastNoise_C.cpp:221-239) leaves the generated source -- the cubin cache key -- unchanged and only moves a value of the kernel's
+    parameter argument. Integers / enums, and floats the lowering looks at to pick a code shape, still change the text."""
+    from tests.trees import Tree
+    lib = fn.lib
+    t = Tree(lib)
+    fbm = t.new(13)                      # FractalFBm( Simplex )
+    simplex = t.leaf(6, 37.0)
+    assert lib.fnSetNodeLookup(fbm, 0, simplex)
+    g = fn.Generator(handle=fbm)
+    try:
+        src0, par0 = g.kernel_source(3), g.kernel_params(3).copy()
+        assert "tp[0]" in src0 and "0x1." not in src0.split("// FractalFBm")[1].split("extern")[0]  # no float literal of a parameter in the node functions
+        def set_hybrid(node, name, value):
+            node_id = lib.fnGetMetadataID(node)
+            index = [lib.fnGetMetadataHybridName(node_id, i).decode() for i in range(lib.fnGetMetadataHybridCount(node_id))].index(name)
+            assert lib.fnSetHybridFloat(node, index, value)
+
+        t.set_float(simplex, "Feature Scale", 53.0)
+        set_hybrid(fbm, "Gain", 0.625)
+        t.set_float(fbm, "Lacunarity", 2.5)
+        src1, par1 = g.kernel_source(3), g.kernel_params(3).copy()
+        assert src1 == src0 and len(par1) == len(par0) and not np.array_equal(par0, par1)
+        assert np.float32(0.625) in par1 and np.float32(2.5) in par1 and np.float32(1.0) / np.float32(53.0) in par1
+        t.set_int(fbm, "Octaves", 5)         # structure: a different kernel
+        assert g.kernel_source(3) != src0
+        t.set_int(fbm, "Octaves", 3)
+        assert g.kernel_source(3) == src0
+        set_hybrid(fbm, "Weighted Strength", 0.5)  # 0 -> non-zero switches the weighted-amplitude code on: shape change
+        assert g.kernel_source(3) != src0
+    finally:
+        g.handle = None
+        t.close()

@@ -168,7 +168,7 @@ def test_integer_intermediates_match_the_oracle(gpu, case):
         pytest.skip("oracle/libfn2oracle.so not built")
     n = (96, 64, 48)
     off = (-37.25, 11.5, 3.0) if case != "c3_cellular_far" else (1.0e6, -2.5e6, 7.7e5)
-    step = 1.0 if case != "c1_simplex" else 0.75
+    step = 17.0 if case != "c1_simplex" else 12.75  # frequency 0.01: the grid spans ~16 x 11 x 8 cells
     tree = gpu.TREES["c1_simplex"] if case == "c1_simplex" else gpu.TREES["c3b_cellular_lookup_white"]
     mode = 0 if case == "c1_simplex" else 1
     total = n[0] * n[1] * n[2]
