@@ -483,9 +483,9 @@ def main():
         "config": config_of(args, w, world),
         "run": {"points_per_gpu": points, "total_points": work.total_points, "math": args.math, "output_minmax": [lo, hi],
                 "minmax_reduction": "ncclAllReduce(max) over the accumulator's two unsigned keys, on the launching stream, every step" if world > 1 else "single GPU: none"},
-        "roofline": {"bound": "alu", "achieved": issue_rate, "peak": peak, "unit": "T thread-instructions/s (issue slots)", "frac": issue_rate / peak if peak and issue_rate else None,
-                     "lane_ops_per_s": lane_ops,
-                     "achieved_is": ("thread-instructions per second = %.1f inst/point (%s, ncu smsp__inst_executed x threads/inst; %.1f of them packed FP32 = two lane-operations each) x points / kernel time" % (inst_per_point, name, packed_per_point)) if inst_per_point
+        "roofline": {"bound": "alu", "achieved": lane_ops, "peak": peak, "unit": "Tlane-op/s", "frac": lane_ops / peak if peak and lane_ops else None,
+                     "issue_slot_frac": issue_rate / peak if peak and issue_rate else None,
+                     "achieved_is": ("lane-operations per second = (%.1f thread-inst/point, of which %.1f packed FP32 counted twice -- an FFMA2 holds the dispatch port for two cycles, profiles/r2_alu_probe.txt; %s, ncu smsp__inst_executed x threads/inst) x points / kernel time" % (inst_per_point, packed_per_point, name)) if inst_per_point
                      else "no ncu instruction count of the current kernel is committed for this workload + math mode (%s): see reference_ops" % name,
                      "traffic": traffic, "traffic_source": (name + " (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)") if traffic else None,
                      "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-compiled tree kernel, persistent grid-stride launch)", "kernel_ms": kernel_ms,

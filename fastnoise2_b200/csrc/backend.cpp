@@ -43,6 +43,7 @@ namespace
 {
     constexpr int kBlock = 256;
     constexpr int kItersPerThread = 8; // groups one thread walks in a large call (see Launch)
+    constexpr std::size_t kConvergedCodeBytes = 48 * 1024; // kernels larger than this walk one group per thread (see Launch)
 
     thread_local std::string tLastError;
     std::atomic<int> gMathMode { 0 };
@@ -78,7 +79,31 @@ namespace
         cudaLibrary_t library = nullptr;
         cudaKernel_t kernel = nullptr;
         int residentBlocks = 0; // blocks of kBlock threads the whole device keeps resident: the persistent launch size
+        std::size_t codeBytes = 0; // size of fn2_entry's machine code: what the instruction caches have to hold
     };
+
+    // Size of the section that holds `kernel`'s code in a cubin (ELF64): .text.<kernel>. 0 if it cannot be found.
+    std::size_t KernelCodeBytes( const std::vector<char>& cubin, const char* kernel )
+    {
+        struct Header { unsigned char ident[16]; std::uint16_t type, machine; std::uint32_t version; std::uint64_t entry, phoff, shoff; std::uint32_t flags; std::uint16_t ehsize, phentsize, phnum, shentsize, shnum, shstrndx; };
+        struct Section { std::uint32_t name, type; std::uint64_t flags, addr, offset, size; std::uint32_t link, info; std::uint64_t addralign, entsize; };
+        if( cubin.size() < sizeof( Header ) || std::memcmp( cubin.data(), "\177ELF", 4 ) != 0 || cubin[4] != 2 ) return 0;
+        Header h;
+        std::memcpy( &h, cubin.data(), sizeof( h ) );
+        if( h.shentsize != sizeof( Section ) || h.shoff + (std::uint64_t)h.shnum * sizeof( Section ) > cubin.size() || h.shstrndx >= h.shnum ) return 0;
+        auto section = [&]( unsigned i ) { Section s; std::memcpy( &s, cubin.data() + h.shoff + (std::uint64_t)i * sizeof( Section ), sizeof( s ) ); return s; };
+        const Section names = section( h.shstrndx );
+        if( names.offset + names.size > cubin.size() ) return 0;
+        const std::string want = std::string( ".text." ) + kernel;
+        for( unsigned i = 0; i < h.shnum; i++ )
+        {
+            const Section s = section( i );
+            if( s.name >= names.size ) continue;
+            const char* text = cubin.data() + names.offset + s.name;
+            if( std::strncmp( text, want.c_str(), names.size - s.name ) == 0 ) return (std::size_t)s.size;
+        }
+        return 0;
+    }
 
     std::string CacheDir()
     {
@@ -120,7 +145,7 @@ namespace
     std::vector<std::string> CompileOptions( int mathMode )
     {
         std::vector<std::string> o = {
-            "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
+            "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--ptxas-options=-v",
             "-DFN2_BLOCK=" + std::to_string( kBlock ),
             ( mathMode & 1 ) ? "--fmad=true" : "--fmad=false",
         };
@@ -133,8 +158,27 @@ namespace
         return o;
     }
 
+    std::vector<char> CompileOnce( const std::string& source, int mathMode, const char* extraOption, std::string& error, int* registers );
+
     // NVRTC: source -> cubin (no GPU needed). Empty vector + error text on failure.
+    // Kernels are compiled with __launch_bounds__( 256 ) and no minimum block count: a minimum is an occupancy TARGET that costs the
+    // light trees 3-7 % (profiles/r2_perf_sweep_b_launch_geometry.txt). Left alone, though, ptxas takes 145 registers for SuperSimplex
+    // 4D x 4 points -- one block per SM, -18 % -- so a kernel that comes out above 128 registers is compiled once more with a minimum
+    // of two blocks per SM (a 128-register cap).
     std::vector<char> CompileToCubin( const std::string& source, int mathMode, std::string& error )
+    {
+        int registers = 0;
+        std::vector<char> cubin = CompileOnce( source, mathMode, nullptr, error, &registers );
+        if( !cubin.empty() && registers > 128 )
+        {
+            std::string capError;
+            std::vector<char> capped = CompileOnce( source, mathMode, "-DFN2_LAUNCH_BOUNDS=__launch_bounds__(FN2_BLOCK,2)", capError, nullptr );
+            if( !capped.empty() ) return capped;
+        }
+        return cubin;
+    }
+
+    std::vector<char> CompileOnce( const std::string& source, int mathMode, const char* extraOption, std::string& error, int* registers )
     {
         const int n = kEmbeddedDeviceSourceCount;
         nvrtcProgram prog = nullptr;
@@ -145,6 +189,7 @@ namespace
             return {};
         }
         std::vector<std::string> opts = CompileOptions( mathMode );
+        if( extraOption ) opts.push_back( extraOption );
         std::vector<const char*> optPtrs;
         for( const std::string& s : opts ) optPtrs.push_back( s.c_str() );
         r = nvrtcCompileProgram( prog, (int)optPtrs.size(), optPtrs.data() );
@@ -157,6 +202,16 @@ namespace
             error = std::string( "nvrtcCompileProgram: " ) + nvrtcGetErrorString( r ) + "\n" + log;
             nvrtcDestroyProgram( &prog );
             return {};
+        }
+        if( registers )
+        {
+            // "ptxas info    : Used 64 registers, ..." for fn2_entry, the only kernel of the program
+            std::size_t logSize = 0;
+            nvrtcGetProgramLogSize( prog, &logSize );
+            std::string log( logSize, '\0' );
+            if( logSize ) nvrtcGetProgramLog( prog, &log[0] );
+            const std::size_t at = log.find( "Used " );
+            *registers = at == std::string::npos ? 0 : std::atoi( log.c_str() + at + 5 );
         }
         std::size_t size = 0;
         nvrtcGetCUBINSize( prog, &size );
@@ -251,6 +306,7 @@ namespace
             sms = 148;
         }
         m.residentBlocks = perSm * sms;
+        m.codeBytes = KernelCodeBytes( cubin, "fn2_entry" );
         return &gModules.emplace( std::make_pair( sourceHash, device ), m ).first->second;
     }
 
@@ -309,7 +365,7 @@ namespace
         CopyPool()
         {
             int n = EnvInt( "FASTNOISE2_B200_COPY_THREADS", 0 );
-            if( n <= 0 ) n = (int)std::min<unsigned>( 8, std::max<unsigned>( 2, std::thread::hardware_concurrency() / 2 ) );
+            if( n <= 0 ) n = (int)std::min<unsigned>( 16, std::max<unsigned>( 2, std::thread::hardware_concurrency() / 2 ) );
             for( int i = 0; i < n; i++ )
             {
                 mWorkers.emplace_back( [this]
@@ -685,8 +741,11 @@ namespace FastNoise
             // keeps balancing the SMs to the end of the call. (A grid of exactly the resident blocks, every thread walking the whole
             // call, measured 11 % SLOWER on the heavy trees: warps that the issue arbiter favours finish early and the tail runs
             // under-occupied. profiles/r2_perf_sweep.txt) Never fewer blocks than the device keeps resident.
+            // Above kConvergedCodeBytes of loop body one group per thread: the warps of a block then run through the code together,
+            // one instruction stream per block. Walking several groups they drift apart, every warp fetches its own stream, and the
+            // instruction cache thrashes (terrain tree, 55 KB: ICC hit rate 70 %, "no instruction" the top stall, -11 %).
             const unsigned long long resident = (unsigned long long)std::max( 1, m->residentBlocks );
-            const int iters = EnvInt( "FASTNOISE2_B200_ITERS", kItersPerThread );
+            const int iters = EnvInt( "FASTNOISE2_B200_ITERS", m->codeBytes > kConvergedCodeBytes ? 1 : kItersPerThread );
             blocks = iters <= 0 ? std::min( blocks, resident ) : std::min( blocks, std::max( resident, ( blocks + iters - 1 ) / iters ) );
             if( blocks > 0x7fffffffull )
             {

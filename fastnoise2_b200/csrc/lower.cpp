@@ -783,7 +783,7 @@ namespace
     std::string EntryOpen( const char* argsType, int ppt, bool wide )
     {
         std::ostringstream k;
-        k << "extern \"C\" __global__ void __launch_bounds__( FN2_BLOCK FN2_MIN_BLOCKS_ARG ) fn2_entry" << kEntryHead << argsType
+        k << "extern \"C\" __global__ void FN2_LAUNCH_BOUNDS fn2_entry" << kEntryHead << argsType
           << " a, unsigned* __restrict__ mm, int seed, const FN2_GRID_CONSTANT fn2::TreeParams params )\n{\n"
           << "    const float* __restrict__ tp = params.v;\n"
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
@@ -801,8 +801,7 @@ namespace
               << "    for( unsigned group = blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
               << "        const unsigned first = group * " << ppt << "u;\n";
         }
-        k << "        any = true;\n"
-          << "        FN2_ITERATION_BARRIER\n";
+        k << "        any = true;\n";
         return k.str();
     }
 
@@ -848,27 +847,13 @@ namespace
         {
             k << "        const F p" << kAxis[d] << " = fn2::fma_( fn2::cvt_f( (int)i" << kAxis[d] << " ), a.step[" << d << "], a.off[" << d << "] );\n";
         }
-        k << "#if FN2_ROLL_POINTS && FN2_W == 1\n"
-          // one copy of the tree code, walked once per point: a quarter of the instruction footprint of the unrolled form
-          << "#pragma unroll 1\n"
-          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            const F px = fn2::index_positions<F>( ix + p, a.step[0], a.off[0] );\n"
-          << "            const float v = " << root << "( seed, " << Pos( dim, "p" ) << ", tp );\n"
-          << "            vmin = fn2::min_( vmin, v );\n"
-          << "            vmax = fn2::max_( vmax, v );\n"
-          << "            out[first + p] = v;\n"
-          << "        }\n"
-          << "    }\n"
-          << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n"
-          << "#else\n"
-          << "        float v[" << ppt << "];\n"
+        k << "        float v[" << ppt << "];\n"
           << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p += FN2_W )\n        {\n"
           << "            const F px = fn2::index_positions<F>( ix + p, a.step[0], a.off[0] );\n"
           << "            fn2::spill_lanes( " << root << "( seed, " << Pos( dim, "p" ) << ", tp ), v + p );\n"
           << "        }\n"
-          << EntryClose( ppt )
-          << "#endif\n";
+          << EntryClose( ppt );
         return k.str();
     }
 
@@ -987,11 +972,11 @@ namespace FastNoise
                 << "#define FN2_RELAXED " << ( mathMode & 1 ) << "\n"
                 << "#define FN2_TABLES " << ( ( mathMode & 2 ) ? 0 : 1 ) << "\n"
                 << "#ifndef FN2_BLOCK\n#define FN2_BLOCK 256\n#endif\n"
-                << "#ifndef FN2_MIN_BLOCKS_ARG\n#define FN2_MIN_BLOCKS_ARG\n#endif\n"
+                // backend.cpp recompiles with a minimum of two blocks per SM when ptxas takes more than 128 registers this way
+                << "#ifndef FN2_LAUNCH_BOUNDS\n#define FN2_LAUNCH_BOUNDS __launch_bounds__( FN2_BLOCK )\n#endif\n"
                 << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP " << ( width == 2 ? "_Pragma( \"unroll\" )" : "" ) << "\n#endif\n"
                 << "#define FN2_W " << width << "\n"
-                << "#ifndef FN2_ROLL_POINTS\n#define FN2_ROLL_POINTS 0\n#endif\n"
-                << "#ifndef FN2_ITERATION_BARRIER\n#define FN2_ITERATION_BARRIER\n#endif\n"
+
                 << "#include \"fn2_device.cuh\"\n\n"
                 << "// float node parameters: kernel arguments (one compiled kernel per tree SHAPE) -- " << emitter.params.size() << " in this tree\n"
                 << "namespace fn2 { struct TreeParams { float v[" << std::max<std::size_t>( 1, emitter.params.size() ) << "]; }; }\n"

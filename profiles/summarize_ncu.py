@@ -20,6 +20,11 @@ METRICS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
     "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+    # instruction supply: these kernels are up to 55 KB of straight-line code
+    "sm__icc_request_hit_rate.pct",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
 ]
 UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}
 
@@ -79,19 +84,22 @@ def main():
         m["lane_ops_per_point"] = m["thread_inst_per_point"] + m["packed_thread_inst_per_point"]  # a packed instruction = 2 lane-operations
     json.dump(summary, open(os.path.join(here, "%s_ncu_summary.json" % tag), "w"), indent=1)
     lines = ["# ncu --set full --clock-control none, kernel fn2_entry (one launch per workload), round %s" % tag, "",
-             "| workload | time | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | lsu pipe % | tensor % | thread-inst/point (of which packed) | DRAM read | DRAM write | local ld/st |",
-             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+             "| workload | time | grid | regs | warps active % | issue slots busy % | alu pipe % | fma pipe % | xu pipe % | lsu pipe % | tensor % | thread-inst/point (of which packed) | ICC hit % | stalled no-instruction / not-selected / math-pipe / dispatch (warps per issue) | DRAM read | DRAM write | local ld/st |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for w, m in summary.items():
-        lines.append("| %s%s | %.3f ms | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f (%.1f) | %.3g B | %.3g B | %d/%d |" % (
-            w, " (stale)" if "stale" in m else "", m["gpu__time_duration.sum"] * 1e3, m["launch__registers_per_thread"], m["sm__warps_active.avg.pct_of_peak_sustained_active"],
+        lines.append("| %s%s | %.3f ms | %d | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f (%.1f) | %.1f | %.2f / %.2f / %.2f / %.2f | %.3g B | %.3g B | %d/%d |" % (
+            w, " (stale)" if "stale" in m else "", m["gpu__time_duration.sum"] * 1e3, m.get("launch__grid_size", 0), m["launch__registers_per_thread"], m["sm__warps_active.avg.pct_of_peak_sustained_active"],
             m["smsp__issue_active.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
             m["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"], m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"],
             m.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", 0),
-            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["thread_inst_per_point"], m["packed_thread_inst_per_point"], m.get("dram__bytes_read.sum", 0),
+            m.get("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", 0), m["thread_inst_per_point"], m["packed_thread_inst_per_point"],
+            m.get("sm__icc_request_hit_rate.pct", 0), m.get("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", 0),
+            m.get("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", 0), m.get("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", 0),
+            m.get("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", 0), m.get("dram__bytes_read.sum", 0),
             m.get("dram__bytes_write.sum", 0), m.get("sass__inst_executed_local_loads", 0), m.get("sass__inst_executed_local_stores", 0)))
     if any("stale" in m for m in summary.values()):
-        lines += ["", "(stale): captured before the last change of the kernel source that affects this workload (the hash-multiplier scaling of the table",
-                  "gradients, -53 instructions/point on c4); pipe shares and DRAM bytes still describe the kernel, the instruction count is an upper bound."]
+        lines += ["", "(stale): captured before the last change of the kernel source that affects this workload; pipe shares and DRAM bytes still describe",
+                  "the kernel, the instruction count does not."]
     open(os.path.join(here, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
