@@ -553,9 +553,36 @@ def measure_gather(args, w, work, gen, lib, torch, dist, rank, world, sptr, comm
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     gen_ms, gat_ms = t.tolist()
     inbound = (total - counts[rank]) * 4
-    return {"generate_ms": gen_ms, "gather_ms": gat_ms, "volume_bytes": total * 4, "inbound_bytes_per_gpu": inbound,
-            "inbound_GBps_per_gpu": inbound / (gat_ms * 1e-3) / 1e9, "steps": steps,
-            "api": "fnb200CommGatherSlabs (NCCL all-gather over NVLink), slabs generated in place inside the volume; timed separately from compute"}
+    result = {"generate_ms": gen_ms, "gather_ms": gat_ms, "volume_bytes": total * 4, "inbound_bytes_per_gpu": inbound,
+              "inbound_GBps_per_gpu": inbound / (gat_ms * 1e-3) / 1e9, "steps": steps,
+              "api": "fnb200CommGatherSlabs (NCCL all-gather over NVLink), slabs generated in place inside the volume; timed separately from compute"}
+    del volume, mine
+    # the fused form: the generating kernel stores every value into all ranks' copies (peer memory, CUDA IPC), no gather pass
+    if w["kind"] == "grid3d" and world <= 8:
+        shared = lib.fnb200CommAllocVolume(comm, total, sptr)
+        if shared:
+            def fused():
+                return lib.fnb200GenUniformGrid3DShared(gen.handle, shared, 0.0, 0.0, 0.0, w["n"][0], w["n"][1], w["n"][2], s, s, s, SEED, begin, end, work.mm.data_ptr(), sptr)
+            assert fused() == 0, fn.last_error()
+            lib.fnb200CommAllReduceMinMax(comm, work.mm.data_ptr(), sptr)
+            torch.cuda.synchronize()
+            dist.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(steps):
+                fused()
+                lib.fnb200CommAllReduceMinMax(comm, work.mm.data_ptr(), sptr)  # the cross-rank completion barrier of a step
+            f1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([f0.elapsed_time(f1) / steps], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            result["fused_generate_and_gather_ms"] = t.item()
+            result["fused_outbound_GBps_per_gpu"] = (world - 1) * counts[rank] * 4 / (t.item() * 1e-3) / 1e9
+            result["fused_api"] = "fnb200GenUniformGrid3DShared: peer stores from the generating kernel into every rank's copy (CUDA IPC over NVLink) + min/max all-reduce as the step barrier"
+            lib.fnb200CommFreeVolume(comm, shared, sptr)
+        else:
+            result["fused_error"] = fn.last_error()
+    return result
 
 
 def measure_e2e(args, w, gen, lib, rank, world, work, torch, dist, np, pinned):

@@ -88,6 +88,11 @@ PROTOTYPES = {
     "fnb200CommDestroy": (I, [P]),
     "fnb200CommAllReduceMinMax": (I, [P, P, P]),
     "fnb200CommGatherSlabs": (I, [P, P, P, P, P]),
+    "fnb200CommAllocVolume": (P, [P, LL, P]),
+    "fnb200VolumeData": (P, [P]),
+    "fnb200CommFreeVolume": (I, [P, P, P]),
+    "fnb200VolumeMirrors": (I, [P, LL, P, P, P]),
+    "fnb200GenUniformGrid3DShared": (I, [P, P, F, F, F, I, I, I, F, F, F, I, I, I, P, P]),
 }
 
 

@@ -757,7 +757,7 @@ namespace FastNoise
         }
 
         int LaunchGridRows( const Generator* root, const GridCall& call, float* deviceOut, unsigned long long rowBegin, unsigned long long rowCount,
-                            unsigned* deviceMinMax, cudaStream_t stream )
+                            unsigned* deviceMinMax, cudaStream_t stream, const Mirrors* mirrors )
         {
             const unsigned nx = (unsigned)call.count[0];
             const unsigned long long points = rowCount * nx;
@@ -795,6 +795,11 @@ namespace FastNoise
                 a.vecStore = ( (std::uintptr_t)deviceOut % 16 ) == 0;
                 a.groups = (unsigned)groups;
                 a.divX = MakeFastDiv( nx );
+                for( int k = 0; mirrors && k < mirrors->count && k < 7; k++ )
+                {
+                    a.mirror[a.mirrors++] = mirrors->out[k];
+                    a.vecStore = a.vecStore && ( (std::uintptr_t)mirrors->out[k] % 16 ) == 0;
+                }
                 void* args[] = { &deviceOut, &a, &deviceMinMax, &seed, program.params.data() };
                 return Launch( m, groups, args, stream ) ? 0 : -2;
             }
@@ -813,6 +818,11 @@ namespace FastNoise
             a.divX = MakeFastDiv( nx );
             a.divY = MakeFastDiv( (unsigned)call.count[1] );
             a.divZ = MakeFastDiv( (unsigned)call.count[2] );
+            for( int k = 0; mirrors && k < mirrors->count && k < 7; k++ )
+            {
+                a.mirror[a.mirrors++] = mirrors->out[k];
+                a.vecStore = a.vecStore && ( (std::uintptr_t)mirrors->out[k] % 16 ) == 0;
+            }
             void* args[] = { &deviceOut, &a, &deviceMinMax, &seed, program.params.data() };
             return Launch( m, groups, args, stream ) ? 0 : -2;
         }

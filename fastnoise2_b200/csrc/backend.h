@@ -22,6 +22,8 @@ namespace FastNoise
             int count[4];
             unsigned rowBegin, total, vecStore, groups;
             FastDivHost divX, divY, divZ;
+            float* mirror[7];
+            unsigned mirrors, pad2;
         };
 
         struct TileArgsHost
@@ -30,6 +32,15 @@ namespace FastNoise
             int xSize, ySize;
             unsigned rowBegin, total, vecStore, groups, pad[2];
             FastDivHost divX;
+            float* mirror[7];
+            unsigned mirrors, pad2;
+        };
+
+        /// Copies of the output in other GPUs' memory that a grid launch also writes (fused all-gather over peer memory).
+        struct Mirrors
+        {
+            int count = 0;
+            float* out[7] = {};
         };
 
         struct PosArgsHost
@@ -69,7 +80,7 @@ namespace FastNoise
 
         /// Rows [rowBegin, rowBegin + rowCount) of the full grid into deviceOut (first element = first point of rowBegin). 0 or FNB200_E*.
         int LaunchGridRows( const Generator* root, const GridCall& call, float* deviceOut, unsigned long long rowBegin, unsigned long long rowCount,
-                            unsigned* deviceMinMax, cudaStream_t stream );
+                            unsigned* deviceMinMax, cudaStream_t stream, const Mirrors* mirrors = nullptr );
         int LaunchPositions( const Generator* root, int dims, float* deviceOut, unsigned long long count, const float* const pos[4],
                              const float offset[4], int seed, unsigned* deviceMinMax, cudaStream_t stream );
 

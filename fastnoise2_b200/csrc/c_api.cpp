@@ -271,8 +271,20 @@ extern "C"
         return FNB200_OK;
     }
 
-    static int SlabLaunch( const void* node, Impl::GridCall& call, int outerAxis, float* deviceOut, int slabBegin, int slabEnd, void* deviceMinMax, void* stream )
+    static int SlabLaunch( const void* node, Impl::GridCall& call, int outerAxis, float* deviceOut, int slabBegin, int slabEnd, void* deviceMinMax, void* stream, void* sharedVolume = nullptr )
     {
+        Impl::Mirrors mirrors;
+        if( sharedVolume )
+        {
+            // the slab is generated at its place inside the shared volume and stored into every rank's copy
+            long long first = slabBegin;
+            for( int d = 0; d < outerAxis; d++ ) first *= call.count[d];
+            if( slabBegin < 0 || fnb200VolumeMirrors( sharedVolume, first, &deviceOut, mirrors.out, &mirrors.count ) != FNB200_OK )
+            {
+                Impl::SetLastError( "shared-volume call: bad volume or slab" );
+                return FNB200_EINVAL;
+            }
+        }
         if( !node || !deviceOut || slabBegin < 0 || slabEnd > call.count[outerAxis] || slabBegin >= slabEnd )
         {
             Impl::SetLastError( "slab call: bad node, output or slab range" );
@@ -289,7 +301,7 @@ extern "C"
             }
         }
         return Impl::LaunchGridRows( Gen( node ), call, deviceOut, rowsPerOuter * (unsigned)slabBegin, rowsPerOuter * (unsigned)( slabEnd - slabBegin ),
-                                     (unsigned*)deviceMinMax, StreamOf( stream ) );
+                                     (unsigned*)deviceMinMax, StreamOf( stream ), sharedVolume ? &mirrors : nullptr );
     }
 
     static Impl::GridCall EmptyCall( int kind, int seed )
@@ -319,6 +331,22 @@ extern "C"
         c.count[0] = xCount; c.count[1] = yCount; c.count[2] = zCount;
         c.step[0] = xStepSize; c.step[1] = yStepSize; c.step[2] = zStepSize;
         return SlabLaunch( node, c, 2, deviceOut, slabBegin, slabEnd, deviceMinMax, stream );
+    }
+
+    int fnb200GenUniformGrid3DShared( const void* node, void* sharedVolume, float xOffset, float yOffset, float zOffset, int xCount, int yCount, int zCount,
+                                      float xStepSize, float yStepSize, float zStepSize, int seed, int slabBegin, int slabEnd, void* deviceMinMax, void* stream )
+    {
+        Impl::GridCall c = EmptyCall( Impl::kGrid3D, seed );
+        c.offset[0] = xOffset; c.offset[1] = yOffset; c.offset[2] = zOffset;
+        c.count[0] = xCount; c.count[1] = yCount; c.count[2] = zCount;
+        c.step[0] = xStepSize; c.step[1] = yStepSize; c.step[2] = zStepSize;
+        if( !sharedVolume )
+        {
+            Impl::SetLastError( "fnb200GenUniformGrid3DShared: null volume" );
+            return FNB200_EINVAL;
+        }
+        float* placeholder = reinterpret_cast<float*>( sharedVolume ); // replaced by the slab's address inside the volume
+        return SlabLaunch( node, c, 2, placeholder, slabBegin, slabEnd, deviceMinMax, stream, sharedVolume );
     }
 
     int fnb200GenUniformGrid4D( const void* node, float* deviceOut, float xOffset, float yOffset, float zOffset, float wOffset,

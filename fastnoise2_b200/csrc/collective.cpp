@@ -11,6 +11,7 @@
 #include <cuda_runtime_api.h>
 #include <dlfcn.h>
 
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -142,6 +143,86 @@ extern "C"
         if( !comm || !deviceMinMax ) return Fail( "fnb200CommAllReduceMinMax: null communicator or accumulator", FNB200_EINVAL );
         // the accumulator holds order-preserving keys of -min and +max (zero = empty): MAX over ranks reduces both
         return Rc( nccl, nccl.AllReduce( deviceMinMax, deviceMinMax, 2, ncclUint32Value, ncclMaxValue, static_cast<ncclComm_t>( comm ), (cudaStream_t)stream ), "ncclAllReduce" );
+    }
+
+    // ------------------------------------------------------------------ fused generate + all-gather over peer memory
+    // A "shared volume" is one buffer of `floats` floats on every rank, each allocated by this library (cudaMalloc) and mapped
+    // into every other rank through CUDA IPC, so a rank's generating kernel can store its slab into ALL copies as it produces it
+    // (NVLink P2P stores): the all-gather costs no pass of its own. Collective: every rank of `comm` calls it with the same size.
+    struct SharedVolume
+    {
+        int world = 0, rank = 0;
+        long long floats = 0;
+        float* copy[8] = {}; // copy[rank] is local, the others are peers' memory
+    };
+
+    void* fnb200CommAllocVolume( void* comm, long long floats, void* stream )
+    {
+        Nccl& nccl = Library();
+        if( !nccl.handle ) { Fail( nccl.error ); return nullptr; }
+        if( !comm || floats <= 0 ) { Fail( "fnb200CommAllocVolume: bad argument", FNB200_EINVAL ); return nullptr; }
+        ncclComm_t c = static_cast<ncclComm_t>( comm );
+        std::unique_ptr<SharedVolume> v( new SharedVolume );
+        if( Rc( nccl, nccl.CommCount( c, &v->world ), "ncclCommCount" ) || Rc( nccl, nccl.CommUserRank( c, &v->rank ), "ncclCommUserRank" ) ) return nullptr;
+        if( v->world > 8 ) { Fail( "fnb200CommAllocVolume: at most 8 ranks", FNB200_EINVAL ); return nullptr; }
+        v->floats = floats;
+        cudaStream_t s = (cudaStream_t)stream;
+        cudaIpcMemHandle_t mine;
+        cudaIpcMemHandle_t* gathered = nullptr; // device staging for the handle exchange
+        std::vector<cudaIpcMemHandle_t> all( v->world );
+        bool ok = cudaMalloc( (void**)&v->copy[v->rank], (size_t)floats * sizeof( float ) ) == cudaSuccess &&
+                  cudaIpcGetMemHandle( &mine, v->copy[v->rank] ) == cudaSuccess &&
+                  cudaMalloc( (void**)&gathered, sizeof( mine ) * v->world ) == cudaSuccess &&
+                  cudaMemcpyAsync( gathered + v->rank, &mine, sizeof( mine ), cudaMemcpyHostToDevice, s ) == cudaSuccess;
+        if( ok ) ok = Rc( nccl, nccl.AllGather( gathered + v->rank, gathered, sizeof( mine ), 0 /* ncclInt8 */, c, s ), "ncclAllGather(ipc handles)" ) == FNB200_OK;
+        ok = ok && cudaMemcpyAsync( all.data(), gathered, sizeof( mine ) * v->world, cudaMemcpyDeviceToHost, s ) == cudaSuccess && cudaStreamSynchronize( s ) == cudaSuccess;
+        for( int r = 0; ok && r < v->world; r++ )
+        {
+            if( r != v->rank ) ok = cudaIpcOpenMemHandle( (void**)&v->copy[r], all[r], cudaIpcMemLazyEnablePeerAccess ) == cudaSuccess;
+        }
+        if( gathered ) cudaFree( gathered );
+        if( !ok )
+        {
+            Fail( std::string( "fnb200CommAllocVolume: " ) + cudaGetErrorString( cudaGetLastError() ) );
+            for( int r = 0; r < v->world; r++ ) if( v->copy[r] && r != v->rank ) cudaIpcCloseMemHandle( v->copy[r] );
+            if( v->copy[v->rank] ) cudaFree( v->copy[v->rank] );
+            return nullptr;
+        }
+        return v.release();
+    }
+
+    float* fnb200VolumeData( void* volume ) { return volume ? static_cast<SharedVolume*>( volume )->copy[static_cast<SharedVolume*>( volume )->rank] : nullptr; }
+
+    int fnb200CommFreeVolume( void* comm, void* volume, void* stream )
+    {
+        Nccl& nccl = Library();
+        if( !nccl.handle || !comm || !volume ) return FNB200_EINVAL;
+        std::unique_ptr<SharedVolume> v( static_cast<SharedVolume*>( volume ) );
+        for( int r = 0; r < v->world; r++ ) if( r != v->rank && v->copy[r] ) cudaIpcCloseMemHandle( v->copy[r] );
+        // nobody may still be writing into my copy: a barrier (1-element all-reduce) before the owner frees it
+        unsigned* token = nullptr;
+        if( cudaMalloc( (void**)&token, sizeof( unsigned ) ) == cudaSuccess )
+        {
+            cudaMemsetAsync( token, 0, sizeof( unsigned ), (cudaStream_t)stream );
+            nccl.AllReduce( token, token, 1, ncclUint32Value, ncclMaxValue, static_cast<ncclComm_t>( comm ), (cudaStream_t)stream );
+            cudaStreamSynchronize( (cudaStream_t)stream );
+            cudaFree( token );
+        }
+        cudaFree( v->copy[v->rank] );
+        cudaGetLastError();
+        return FNB200_OK;
+    }
+
+    // Elements [firstFloat, firstFloat + n) of every copy: where a launch that starts at `firstFloat` of the volume must store
+    int fnb200VolumeMirrors( void* volume, long long firstFloat, float** local, float** mirrors /* [7] */, int* mirrorCount )
+    {
+        if( !volume || !local || !mirrors || !mirrorCount ) return FNB200_EINVAL;
+        SharedVolume* v = static_cast<SharedVolume*>( volume );
+        if( firstFloat < 0 || firstFloat > v->floats ) return FNB200_EINVAL;
+        *local = v->copy[v->rank] + firstFloat;
+        *mirrorCount = 0;
+        for( int r = 0; r < v->world; r++ ) if( r != v->rank ) mirrors[( *mirrorCount )++] = v->copy[r] + firstFloat;
+        return FNB200_OK;
     }
 
     int fnb200CommGatherSlabs( void* comm, const float* deviceSlab, float* deviceVolume, const long long* floatsPerRank, void* stream )

@@ -23,6 +23,11 @@ namespace fn2
         u32 vecStore;   // 1: output pointer is 16-byte aligned, vector stores allowed
         u32 groups;     // total / points per thread: the grid-stride loop bound
         FastDiv divX, divY, divZ;
+        // Fused all-gather: the same elements are also stored, as they are produced, into the copies of the volume that other GPUs
+        // hold (peer memory over NVLink; fnb200GenUniformGrid*Shared). mirror[k] points at THIS launch's first element in copy k.
+        float* mirror[7];
+        u32 mirrors;
+        u32 pad2;
     };
 
     struct TileArgs
@@ -35,6 +40,9 @@ namespace fn2
         u32 groups;
         u32 pad[2];
         FastDiv divX;
+        float* mirror[7];
+        u32 mirrors;
+        u32 pad2;
     };
 
     struct PosArgs

@@ -814,6 +814,7 @@ namespace
           << "            vmax = fn2::max_( vmax, v[p] );\n"
           << "        }\n"
           << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
+          << "        for( unsigned k = 0; k < a.mirrors; k++ ) fn2::store_points<" << ppt << ">( a.mirror[k], first, v, a.vecStore != 0 ); // fused all-gather: peer copies\n"
           << "    }\n"
           << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n";
         return k.str();

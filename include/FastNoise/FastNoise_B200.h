@@ -131,6 +131,19 @@ FASTNOISE_API int fnb200CommDestroy( void* comm );
 FASTNOISE_API int fnb200CommAllReduceMinMax( void* comm, void* deviceMinMax, void* stream );
 FASTNOISE_API int fnb200CommGatherSlabs( void* comm, const float* deviceSlab, float* deviceVolume, const long long* floatsPerRank, void* stream );
 
+/* Fused generate + all-gather. A shared volume is one buffer of `floats` floats per rank, allocated by the library and mapped into every
+ * other rank (CUDA IPC over NVLink; at most 8 ranks of one node). fnb200GenUniformGrid3DShared generates this rank's z-slab at its place
+ * in the volume and stores every value into ALL ranks' copies as it is produced (peer stores from the generating kernel), so no separate
+ * gather pass exists. A rank may read the whole volume once every rank's kernel has finished -- e.g. after fnb200CommAllReduceMinMax on
+ * the same stream, which completes only when all ranks have reached it. Alloc / Free are collective (all ranks, same size). */
+FASTNOISE_API void* fnb200CommAllocVolume( void* comm, long long floats, void* stream );
+FASTNOISE_API float* fnb200VolumeData( void* sharedVolume );          /* this rank's copy (device pointer) */
+FASTNOISE_API int fnb200CommFreeVolume( void* comm, void* sharedVolume, void* stream );
+FASTNOISE_API int fnb200VolumeMirrors( void* sharedVolume, long long firstFloat, float** local, float** mirrors /* [7] */, int* mirrorCount );
+FASTNOISE_API int fnb200GenUniformGrid3DShared( const void* node, void* sharedVolume, float xOffset, float yOffset, float zOffset,
+                                                int xCount, int yCount, int zCount, float xStepSize, float yStepSize, float zStepSize,
+                                                int seed, int slabBegin, int slabEnd, void* deviceMinMax, void* stream );
+
 /* Number of kernels this library has launched in the calling process (all threads). */
 FASTNOISE_API unsigned long long fnb200LaunchCount( void );
 

@@ -118,6 +118,22 @@ def _rank_main(rank, world, port, tmp):
         assert lib.fnb200CommGatherSlabs(comm, slab.data_ptr(), volume2.data_ptr(), (ctypes.c_longlong * world)(*counts), sp) == 0, fn.last_error()
     stream.synchronize()
     assert torch.equal(volume2, whole)
+    # fused generate + all-gather: every rank's kernel stores its slab into ALL ranks' copies of a shared volume (peer memory)
+    shared = lib.fnb200CommAllocVolume(comm, per * n[2], sp)
+    assert shared, fn.last_error()
+    with torch.cuda.stream(stream):
+        assert lib.fnb200MinMaxReset(acc.data_ptr(), sp) == 0
+        assert lib.fnb200GenUniformGrid3DShared(g.handle, shared, 0.0, 0.0, 0.0, n[0], n[1], n[2], 2.7, 2.7, 2.7, 1337, begin, end, acc.data_ptr(), sp) == 0, fn.last_error()
+        assert lib.fnb200CommAllReduceMinMax(comm, acc.data_ptr(), sp) == 0  # also the cross-rank barrier: every slab has landed
+        mm3 = np.zeros(2, np.float32)
+        assert lib.fnb200MinMaxRead(acc.data_ptr(), sp, mm3.ctypes.data) == 0
+        got = torch.empty_like(whole)
+        import ctypes as ct
+        ct.cdll.LoadLibrary("libcudart.so.12").cudaMemcpyAsync(ct.c_void_p(got.data_ptr()), ct.c_void_p(lib.fnb200VolumeData(shared)), ct.c_size_t(per * n[2] * 4), 3, ct.c_void_p(sp))
+    stream.synchronize()
+    assert torch.equal(got, whole), "shared volume differs on rank %d" % rank
+    assert (float(mm3[0]), float(mm3[1])) == mm_whole
+    assert lib.fnb200CommFreeVolume(comm, shared, sp) == 0
     assert lib.fnb200CommDestroy(comm) == 0
     dist.destroy_process_group()
     open(os.path.join(tmp, "rank%d.ok" % rank), "w").write("ok")

@@ -4,6 +4,7 @@ Values that are not finite, enum members that are out of range and cell coordina
 offline host-emulation fuzz (tests/test_host_emulation.py) found differences in, now pinned. The same
 cases run on the CPU against the generated code in tests/test_host_emulation.py.
 """
+import numpy as np
 import pytest
 
 from tests import helpers
@@ -62,3 +63,44 @@ def test_convert_overflow_regime_matches_the_saturating_port(gpu, port):
             assert same(got, want), (text, helpers.compare(got, want))
     finally:
         port.fn2oSetConvertMode(0)
+
+
+def test_short_lived_caller_threads_do_not_leak_device_memory(gpu):
+    """Each calling thread owns streams and staging buffers per device; they are released when the thread exits (a consumer that
+    spawns worker threads per chunk -- the Node Editor's mesh preview does -- must not lose 128 MiB of HBM per thread)."""
+    import threading
+    import torch
+    g = gpu.Generator(gpu.TREES["c1_simplex"])
+    n = 96
+
+    def work(results, index):
+        out = np.empty(n ** 3, np.float32)
+        results[index] = g.grid3d(out, float(index), 0.0, 0.0, n, n, n, 1.0, 1.0, 1.0, 1337)
+
+    def churn(count):
+        results = [None] * count
+        for i in range(count):
+            t = threading.Thread(target=work, args=(results, i))
+            t.start()
+            t.join()
+        assert all(r is not None and r[0] < r[1] for r in results)
+
+    churn(3)
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info()
+    churn(24)
+    torch.cuda.synchronize()
+    free_after, _ = torch.cuda.mem_get_info()
+    assert free_before - free_after < 16 << 20, (free_before, free_after)
+
+
+def test_grid_limits_are_refused_not_miscomputed(gpu):
+    """Index arithmetic is exact below 2^31 rows / points; anything larger is refused with an error (never silently decomposed wrongly)."""
+    import torch
+    g = gpu.Generator(gpu.TREES["c1_simplex"])
+    out = torch.empty(16, dtype=torch.float32, device="cuda")
+    rc = gpu.lib.fnb200GenUniformGrid3D(g.handle, out.data_ptr(), 0.0, 0.0, 0.0, 1, 65536, 65536, 1.0, 1.0, 1.0, 1337, 40000, 40001, None, None)
+    assert rc == -1 and "2^31" in gpu.last_error()
+    mm = np.zeros(2, np.float32)
+    gpu.lib.fnGenUniformGrid4D(g.handle, out.data_ptr(), 0.0, 0.0, 0.0, 0.0, 65536, 65536, 65536, 65536, 1.0, 1.0, 1.0, 1.0, 1337, mm.ctypes.data)
+    assert mm[0] > mm[1] and "2^31" in gpu.last_error()
