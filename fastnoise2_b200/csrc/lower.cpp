@@ -61,6 +61,19 @@ namespace
 
     const char* const kAxis[4] = { "x", "y", "z", "w" };
 
+    int EnvFlag( const char* name, int fallback )
+    {
+        const char* v = std::getenv( name );
+        return v && *v ? std::atoi( v ) : fallback;
+    }
+
+    // Code-shape options of the generated text (each measured on B200, profiles/r2_perf_sweep_c_code_shape.txt). Both are bit-neutral.
+    //   one-body loops: a fractal's first octave runs inside its octave loop, so the source sub-tree appears once in the code
+    //   convergent walk: every thread of a block runs the same number of groups (threads past the end re-evaluate the last group
+    //                    and skip the store), so the loop control and everything uniform inside it stays on the uniform datapath
+    bool OneBodyLoops() { return EnvFlag( "FASTNOISE2_B200_ONE_BODY", 1 ) != 0; }
+    bool ConvergentWalk() { return EnvFlag( "FASTNOISE2_B200_CONVERGENT", 1 ) != 0; }
+
     // "x, y, z"
     std::string Pos( int dim, const char* prefix = "" )
     {
@@ -442,22 +455,40 @@ namespace
                 if( ridged ) sample = "fn2::abs_( " + sample + " )";
                 b << "    const F gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
                 if( weighted ) b << "    const F weightedStrength = " << Hyb( g, 1, dim, "seed", P ) << ";\n";
-                b << "    F amp = 1.0f;\n";
-                b << "    F noise = " << sample << ";\n";
-                b << "    F sum = " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
-                if( octaves > 1 )
+                const std::string term = ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp";
+                const std::string lacunarity = Par( s.f[F_K0] );
+                auto nextOctave = [&]( const char* indent )
                 {
-                    b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
-                    b << "        seed = fn2::iadd( seed, 1 );\n";
-                    if( weighted ) b << "        amp *= fn2::lerp( 1.0f, " << ( ridged ? "1.0f - noise" : "( noise + 1.0f ) * 0.5f" ) << ", weightedStrength );\n";
-                    b << "        amp *= gain;\n";
-                    {
-                        const std::string lacunarity = Par( s.f[F_K0] );
-                        for( int d = 0; d < dim; d++ ) b << "        " << kAxis[d] << " *= " << lacunarity << ";\n";
-                    }
+                    b << indent << "seed = fn2::iadd( seed, 1 );\n";
+                    if( weighted ) b << indent << "amp *= fn2::lerp( 1.0f, " << ( ridged ? "1.0f - noise" : "( noise + 1.0f ) * 0.5f" ) << ", weightedStrength );\n";
+                    b << indent << "amp *= gain;\n";
+                    for( int d = 0; d < dim; d++ ) b << indent << kAxis[d] << " *= " << lacunarity << ";\n";
+                };
+                b << "    F amp = 1.0f;\n";
+                if( OneBodyLoops() && octaves > 1 )
+                {
+                    // One copy of the source in the code instead of two (first octave + loop body): the first octave runs inside
+                    // the loop. sum starts at -0.0f, the identity of IEEE addition for EVERY addend (-0 + v == v bit for bit, signed
+                    // zeros included), so the first `sum +=` is the reference's `sum = noise * amp`.
+                    b << "    F noise;\n    F sum = -0.0f;\n";
+                    b << "    int octave = 0;\n    FN2_ONE_BODY_LOOP\n    do\n    {\n";
                     b << "        noise = " << sample << ";\n";
-                    b << "        sum += " << ( ridged ? "( noise * -2.0f + 1.0f ) * amp" : "noise * amp" ) << ";\n";
-                    b << "    }\n";
+                    b << "        sum += " << term << ";\n";
+                    nextOctave( "        " ); // also after the last octave (unused there): a conditional step would be peeled into a second copy
+                    b << "    } while( ++octave < " << octaves << " );\n";
+                }
+                else
+                {
+                    b << "    F noise = " << sample << ";\n";
+                    b << "    F sum = " << term << ";\n";
+                    if( octaves > 1 )
+                    {
+                        b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
+                        nextOctave( "        " );
+                        b << "        noise = " << sample << ";\n";
+                        b << "        sum += " << term << ";\n";
+                        b << "    }\n";
+                    }
                 }
                 b << "    return sum;\n";
                 break;
@@ -504,17 +535,33 @@ namespace
                 b << "    int seedInc = seed;\n";
                 b << "    const F gain = " << Hyb( g, 0, dim, "seed", P ) << ";\n";
                 if( independent ) for( int d = 0; d < dim; d++ ) b << "    const F n" << kAxis[d] << " = " << kAxis[d] << ";\n";
-                b << "    F strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << ", tp );\n";
-                if( octaves > 1 )
+                const std::string warpCall = warp + "( seedInc, amp, " + Scaled( dim, "freq", independent ? "n" : "" ) + ", " + P + ", tp )";
+                auto nextWarpOctave = [&]( const char* indent )
                 {
-                    b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
-                    if( weighted ) b << "        strength = fn2::fast_length_sqrt( strength );\n";
-                    b << "        seedInc = fn2::iadd( seedInc, 1 );\n";
-                    b << "        freq *= " << Par( s.f[F_K0] ) << ";\n";
-                    if( weighted ) b << "        amp *= fn2::lerp( 1.0f, 1.0f - strength, weightedStrength );\n";
-                    b << "        amp *= gain;\n";
-                    b << "        strength = " << warp << "( seedInc, amp, " << Scaled( dim, "freq", independent ? "n" : "" ) << ", " << P << ", tp );\n";
-                    b << "    }\n";
+                    if( weighted ) b << indent << "strength = fn2::fast_length_sqrt( strength );\n";
+                    b << indent << "seedInc = fn2::iadd( seedInc, 1 );\n";
+                    b << indent << "freq *= " << Par( s.f[F_K0] ) << ";\n";
+                    if( weighted ) b << indent << "amp *= fn2::lerp( 1.0f, 1.0f - strength, weightedStrength );\n";
+                    b << indent << "amp *= gain;\n";
+                };
+                if( OneBodyLoops() && octaves > 1 )
+                {
+                    b << "    F strength;\n";
+                    b << "    int octave = 0;\n    FN2_ONE_BODY_LOOP\n    do\n    {\n";
+                    b << "        strength = " << warpCall << ";\n";
+                    nextWarpOctave( "        " );
+                    b << "    } while( ++octave < " << octaves << " );\n";
+                }
+                else
+                {
+                    b << "    F strength = " << warpCall << ";\n";
+                    if( octaves > 1 )
+                    {
+                        b << "    FN2_OCTAVE_LOOP\n    for( int octave = 1; octave < " << octaves << "; octave++ )\n    {\n";
+                        nextWarpOctave( "        " );
+                        b << "        strength = " << warpCall << ";\n";
+                        b << "    }\n";
+                    }
                 }
                 b << "    (void)strength;\n";
                 b << "    return " << Src( warpNode, 0, dim, "seed", P ) << ";\n";
@@ -789,32 +836,36 @@ namespace
           << "    float vmin = FN2_INF, vmax = -FN2_INF;\n"
           << "    bool any = false;\n"
           << "    fn2::stage_tables();\n";
-        if( wide )
+        const char* T = wide ? "unsigned long long" : "unsigned";
+        k << "    const " << T << " stride = (" << T << ")gridDim.x * FN2_BLOCK;\n";
+        if( ConvergentWalk() )
         {
-            k << "    const unsigned long long stride = (unsigned long long)gridDim.x * FN2_BLOCK;\n"
-              << "    for( unsigned long long group = (unsigned long long)blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
-              << "        const unsigned long long first = group * " << ppt << "u;\n";
+            k << "    for( " << T << " base = (" << T << ")blockIdx.x * FN2_BLOCK; base < a.groups; base += stride )\n    {\n"
+              << "        const bool live = base + threadIdx.x < a.groups;\n"
+              << "        const " << T << " group = live ? base + threadIdx.x : a.groups - 1;\n";
         }
         else
         {
-            k << "    const unsigned stride = gridDim.x * FN2_BLOCK;\n"
-              << "    for( unsigned group = blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
-              << "        const unsigned first = group * " << ppt << "u;\n";
+            k << "    for( " << T << " group = (" << T << ")blockIdx.x * FN2_BLOCK + threadIdx.x; group < a.groups; group += stride )\n    {\n"
+              << "        const bool live = true;\n";
         }
-        k << "        any = true;\n";
+        k << "        const " << T << " first = group * " << ppt << "u;\n"
+          << "        any = any || live;\n";
         return k.str();
     }
 
     std::string EntryClose( int ppt )
     {
         std::ostringstream k;
-        k << "#pragma unroll\n"
-          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            vmin = fn2::min_( vmin, v[p] );\n"
-          << "            vmax = fn2::max_( vmax, v[p] );\n"
+        k << "        if( live )\n        {\n"
+          << "#pragma unroll\n"
+          << "            for( int p = 0; p < " << ppt << "; p++ )\n            {\n"
+          << "                vmin = fn2::min_( vmin, v[p] );\n"
+          << "                vmax = fn2::max_( vmax, v[p] );\n"
+          << "            }\n"
+          << "            fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
+          << "            for( unsigned k = 0; k < a.mirrors; k++ ) fn2::store_points<" << ppt << ">( a.mirror[k], first, v, a.vecStore != 0 ); // fused all-gather: peer copies\n"
           << "        }\n"
-          << "        fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
-          << "        for( unsigned k = 0; k < a.mirrors; k++ ) fn2::store_points<" << ppt << ">( a.mirror[k], first, v, a.vecStore != 0 ); // fused all-gather: peer copies\n"
           << "    }\n"
           << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n";
         return k.str();
@@ -916,12 +967,12 @@ namespace
           << "        }\n"
           << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            if( first + p < a.count )\n            {\n"
+          << "            if( live && first + p < a.count )\n            {\n"
           << "                vmin = fn2::min_( vmin, v[p] );\n"
           << "                vmax = fn2::max_( vmax, v[p] );\n"
           << "            }\n"
           << "        }\n"
-          << "        if( full )\n        {\n"
+          << "        if( !live )\n        {\n        }\n        else if( full )\n        {\n"
           << "            fn2::store_points<" << ppt << ">( out + first, 0u, v, a.vecIO != 0 );\n"
           << "        }\n        else\n        {\n"
           << "            for( int p = 0; p < " << ppt << "; p++ ) if( first + p < a.count ) out[first + p] = v[p];\n"
@@ -976,6 +1027,8 @@ namespace FastNoise
                 // backend.cpp recompiles with a minimum of two blocks per SM when ptxas takes more than 128 registers this way
                 << "#ifndef FN2_LAUNCH_BOUNDS\n#define FN2_LAUNCH_BOUNDS __launch_bounds__( FN2_BLOCK )\n#endif\n"
                 << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP " << ( width == 2 ? "_Pragma( \"unroll\" )" : "" ) << "\n#endif\n"
+                // one-body loops stay rolled: unrolling or peeling them would bring the second copy of the source back
+                << "#ifndef FN2_ONE_BODY_LOOP\n#define FN2_ONE_BODY_LOOP " << ( EnvFlag( "FASTNOISE2_B200_ONE_BODY", 1 ) == 2 ? "" : "_Pragma( \"unroll 1\" )" ) << "\n#endif\n"
                 << "#define FN2_W " << width << "\n"
 
                 << "#include \"fn2_device.cuh\"\n\n"

@@ -48,7 +48,7 @@ os.environ["FASTNOISE2_B200_FANOUT"] = "1024"
 launches = fn.lib.fnb200LaunchCount()
 fan = np.empty(total, np.float32)                      # pageable: bounce buffers + copy workers, on every device
 mm_fan = g.grid3d(fan, 0.5, -3.0, 7.0, *n, 1.3, 1.3, 1.3, 1337)
-assert fn.lib.fnb200LaunchCount() - launches >= 2 * torch.cuda.device_count()
+assert fn.lib.fnb200LaunchCount() - launches >= torch.cuda.device_count()  # every device took a share (one 4 MB chunk each on 8 GPUs)
 pin = torch.empty(total, dtype=torch.float32, pin_memory=True)
 mm_pin = g.grid3d(pin, 0.5, -3.0, 7.0, *n, 1.3, 1.3, 1.3, 1337)
 assert mm_one == mm_fan == mm_pin, (mm_one, mm_fan, mm_pin)
