@@ -41,7 +41,7 @@ using namespace FastNoise::Impl;
 
 namespace
 {
-    constexpr int kBlock = 256;
+    constexpr int kDefaultBlock = 256;
     constexpr int kItersPerThread = 8; // groups one thread walks in a large call (see Launch)
     constexpr std::size_t kConvergedCodeBytes = 48 * 1024; // kernels larger than this walk one group per thread (see Launch)
 
@@ -73,12 +73,24 @@ namespace
         return v && *v ? std::atoi( v ) : fallback;
     }
 
+    // Threads per block of the entry kernels (FN2_BLOCK in the generated text). 256 from measurements
+    // (profiles/r2_perf_sweep_c_code_shape.txt); FASTNOISE2_B200_BLOCK, read once, overrides it for A/B runs.
+    int BlockThreads()
+    {
+        static const int value = []
+        {
+            const int v = EnvInt( "FASTNOISE2_B200_BLOCK", kDefaultBlock );
+            return v == 64 || v == 128 || v == 512 || v == 1024 ? v : kDefaultBlock;
+        }();
+        return value;
+    }
+
     // ------------------------------------------------------------------ compiled-kernel cache
     struct Module
     {
         cudaLibrary_t library = nullptr;
         cudaKernel_t kernel = nullptr;
-        int residentBlocks = 0; // blocks of kBlock threads the whole device keeps resident: the persistent launch size
+        int residentBlocks = 0; // blocks of BlockThreads() threads the whole device keeps resident: the persistent launch size
         std::size_t codeBytes = 0; // size of fn2_entry's machine code: what the instruction caches have to hold
     };
 
@@ -146,7 +158,7 @@ namespace
     {
         std::vector<std::string> o = {
             "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--ptxas-options=-v",
-            "-DFN2_BLOCK=" + std::to_string( kBlock ),
+            "-DFN2_BLOCK=" + std::to_string( BlockThreads() ),
             ( mathMode & 1 ) ? "--fmad=true" : "--fmad=false",
         };
         if( const char* extra = std::getenv( "FASTNOISE2_B200_NVRTC_FLAGS" ) )
@@ -295,7 +307,7 @@ namespace
             return nullptr;
         }
         int perSm = 0, sms = 0;
-        if( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, (const void*)m.kernel, kBlock, 0 ) != cudaSuccess || perSm < 1 )
+        if( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, (const void*)m.kernel, BlockThreads(), 0 ) != cudaSuccess || perSm < 1 )
         {
             cudaGetLastError();
             perSm = 2;
@@ -734,7 +746,8 @@ namespace FastNoise
         // --------------------------------------------------------------- launches (device pointers)
         static bool Launch( const Module* m, unsigned long long groups, void** args, cudaStream_t stream )
         {
-            unsigned long long blocks = ( groups + kBlock - 1 ) / kBlock;
+            const unsigned block = (unsigned)BlockThreads();
+            unsigned long long blocks = ( groups + block - 1 ) / block;
             if( blocks == 0 ) return true;
             // Grid-stride launch: every thread walks about kItersPerThread groups, so the per-block work (table staging, the min/max
             // reduction) is paid once per that many groups, while the grid stays many waves deep -- the hardware block scheduler
@@ -753,7 +766,7 @@ namespace FastNoise
                 return false;
             }
             CountLaunch();
-            return Check( cudaLaunchKernel( (const void*)m->kernel, dim3( (unsigned)blocks ), dim3( kBlock ), args, 0, stream ), "cudaLaunchKernel" );
+            return Check( cudaLaunchKernel( (const void*)m->kernel, dim3( (unsigned)blocks ), dim3( block ), args, 0, stream ), "cudaLaunchKernel" );
         }
 
         int LaunchGridRows( const Generator* root, const GridCall& call, float* deviceOut, unsigned long long rowBegin, unsigned long long rowCount,

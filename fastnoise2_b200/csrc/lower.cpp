@@ -71,7 +71,7 @@ namespace
     //   one-body loops: a fractal's first octave runs inside its octave loop, so the source sub-tree appears once in the code
     //   convergent walk: every thread of a block runs the same number of groups (threads past the end re-evaluate the last group
     //                    and skip the store), so the loop control and everything uniform inside it stays on the uniform datapath
-    bool OneBodyLoops() { return EnvFlag( "FASTNOISE2_B200_ONE_BODY", 1 ) != 0; }
+    bool OneBodyLoops() { return EnvFlag( "FASTNOISE2_B200_ONE_BODY", 0 ) != 0; }
     bool ConvergentWalk() { return EnvFlag( "FASTNOISE2_B200_CONVERGENT", 1 ) != 0; }
 
     // "x, y, z"
@@ -841,6 +841,7 @@ namespace
         if( ConvergentWalk() )
         {
             k << "    for( " << T << " base = (" << T << ")blockIdx.x * FN2_BLOCK; base < a.groups; base += stride )\n    {\n"
+              << "        FN2_GROUP_BARRIER\n"
               << "        const bool live = base + threadIdx.x < a.groups;\n"
               << "        const " << T << " group = live ? base + threadIdx.x : a.groups - 1;\n";
         }
@@ -850,19 +851,20 @@ namespace
               << "        const bool live = true;\n";
         }
         k << "        const " << T << " first = group * " << ppt << "u;\n"
-          << "        any = any || live;\n";
+          << "        any = true;\n";
         return k.str();
     }
 
     std::string EntryClose( int ppt )
     {
         std::ostringstream k;
-        k << "        if( live )\n        {\n"
-          << "#pragma unroll\n"
-          << "            for( int p = 0; p < " << ppt << "; p++ )\n            {\n"
-          << "                vmin = fn2::min_( vmin, v[p] );\n"
-          << "                vmax = fn2::max_( vmax, v[p] );\n"
-          << "            }\n"
+        // (a thread past the end holds the values of the call's last group: real points, harmless in the min/max)
+        k << "#pragma unroll\n"
+          << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
+          << "            vmin = fn2::min_( vmin, v[p] );\n"
+          << "            vmax = fn2::max_( vmax, v[p] );\n"
+          << "        }\n"
+          << "        if( live )\n        {\n"
           << "            fn2::store_points<" << ppt << ">( out, first, v, a.vecStore != 0 );\n"
           << "            for( unsigned k = 0; k < a.mirrors; k++ ) fn2::store_points<" << ppt << ">( a.mirror[k], first, v, a.vecStore != 0 ); // fused all-gather: peer copies\n"
           << "        }\n"
@@ -967,7 +969,7 @@ namespace
           << "        }\n"
           << "#pragma unroll\n"
           << "        for( int p = 0; p < " << ppt << "; p++ )\n        {\n"
-          << "            if( live && first + p < a.count )\n            {\n"
+          << "            if( first + p < a.count )\n            {\n"
           << "                vmin = fn2::min_( vmin, v[p] );\n"
           << "                vmax = fn2::max_( vmax, v[p] );\n"
           << "            }\n"
@@ -1028,7 +1030,8 @@ namespace FastNoise
                 << "#ifndef FN2_LAUNCH_BOUNDS\n#define FN2_LAUNCH_BOUNDS __launch_bounds__( FN2_BLOCK )\n#endif\n"
                 << "#ifndef FN2_OCTAVE_LOOP\n#define FN2_OCTAVE_LOOP " << ( width == 2 ? "_Pragma( \"unroll\" )" : "" ) << "\n#endif\n"
                 // one-body loops stay rolled: unrolling or peeling them would bring the second copy of the source back
-                << "#ifndef FN2_ONE_BODY_LOOP\n#define FN2_ONE_BODY_LOOP " << ( EnvFlag( "FASTNOISE2_B200_ONE_BODY", 1 ) == 2 ? "" : "_Pragma( \"unroll 1\" )" ) << "\n#endif\n"
+                << "#ifndef FN2_ONE_BODY_LOOP\n#define FN2_ONE_BODY_LOOP " << ( EnvFlag( "FASTNOISE2_B200_ONE_BODY", 0 ) == 2 ? "" : "_Pragma( \"unroll 1\" )" ) << "\n#endif\n"
+                << "#ifndef FN2_GROUP_BARRIER\n#define FN2_GROUP_BARRIER " << ( ConvergentWalk() && EnvFlag( "FASTNOISE2_B200_GROUP_BARRIER", 0 ) ? "__syncthreads();" : "" ) << "\n#endif\n"
                 << "#define FN2_W " << width << "\n"
 
                 << "#include \"fn2_device.cuh\"\n\n"
