@@ -18,7 +18,8 @@ JSON keys: see the task contract. `value` is device-resident throughput (CUDA ev
 launching stream, max over ranks). `e2e` goes through the reference-shaped C ABI call fnGenUniformGrid3D with a
 pinned HOST output buffer: device->host copies are inside the timed region (all K steps). `roofline` is the instruction-issue
 roofline (this path has no tensor work and writes 4 B/point): achieved = thread-instructions the kernel executes per point
-(ncu, profiles/) x points / kernel time, peak = FFMA issue rate measured live by fnb200MeasureAluPeak. `cpu_baseline` = the
+(ncu, profiles/; a packed FP32 instruction counts as the two dispatch cycles it takes) x points / kernel time, peak = the theoretical
+dispatch rate SMs x 4 x 32 x sampled SM clock (the live FFMA probe of fnb200MeasureAluPeak is reported beside it). `cpu_baseline` = the
 reference's own node sources (oracle/_ref, relaxed build = the reference's default flags) on all host cores over a bounded
 sample of the same workload.
 """
@@ -472,7 +473,12 @@ def main():
     # operations of a packed FP32 instruction, the unit the FFMA probe measures
     issue_rate = inst_per_point * points / (kernel_ms * 1e-3) / 1e12 if inst_per_point else None
     lane_ops = (inst_per_point + packed_per_point) * points / (kernel_ms * 1e-3) / 1e12 if inst_per_point else None
-    peak = alu_peak / 1e12
+    # The bound: an SM sub-partition dispatches one warp-instruction (32 lane-operations) per clock; a packed FP32 instruction
+    # holds the dispatch port for two clocks (profiles/r2_alu_probe.txt). Peak = SMs x 4 x 32 x the SM clock sampled under load --
+    # the theoretical dispatch rate, which no instruction mix can exceed; the live FFMA probe (97 % of it) is reported beside it.
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+    peak = sms * 4 * 32 * sm_mhz * 1e6 / 1e12 if sm_mhz else alu_peak / 1e12
     store_gbs = out_bytes / (kernel_ms * 1e-3) / 1e9
     name = os.path.relpath(NCU_SUMMARY, ROOT)
     line = {
@@ -491,7 +497,9 @@ def main():
                      "algorithmic_bytes": out_bytes + in_bytes, "kernel": "fn2_entry (NVRTC-compiled tree kernel, persistent grid-stride launch)", "kernel_ms": kernel_ms,
                      "inst_per_point": inst_per_point,
                      "reference_ops": {"ops_per_point": w["ops"], "tlane_ops_per_s": ref_ops, "note": "SURVEY 8d count of the reference's generic-path SIMD lane-ops; the GPU needs fewer instructions"},
-                     "peak_source": "FFMA issue rate measured live by fnb200MeasureAluPeak (148 SM x 4 schedulers x 32 lanes x clock = the SM issue limit); MEASURED_PEAKS.json has no ALU entry",
+                     "peak_source": ("theoretical dispatch rate: %d SMs x 4 sub-partitions x 32 lanes x %.0f MHz (SM clock sampled during the timed region); MEASURED_PEAKS.json has no ALU entry" % (sms, sm_mhz)) if sm_mhz
+                     else "FFMA issue rate measured live by fnb200MeasureAluPeak (no clock sample available)",
+                     "ffma_probe_tlane_ops_per_s": alu_peak / 1e12,
                      "hbm_store": {"achieved_gbs": store_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": store_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                    "algorithmic_bytes_per_point": 4 + (16 if w["kind"] == "pos4d" else 0)}},
         "cpu_baseline": cpu,

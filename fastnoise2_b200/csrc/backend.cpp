@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
+#if defined( __x86_64__ )
+#include <immintrin.h>
+#endif
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -326,6 +329,44 @@ namespace
     // cudaMemcpyAsync into pageable memory is staged by the driver through one small pinned buffer and runs at a fraction of the
     // link rate. Pageable destinations therefore go device -> pinned bounce buffer (DMA at link rate) -> destination, the second
     // hop done by a few worker threads while the next chunk is computed and transferred.
+    // bounce buffer -> caller's pageable memory. The destination is written once and not read here, so it is written with
+    // non-temporal stores: no read-for-ownership of the destination lines and the bounce buffer stays the only thing in the caches
+    // (glibc's memcpy only switches to streaming stores above a size threshold that the per-worker slices do not always reach).
+#if defined( __x86_64__ )
+    __attribute__(( target( "avx2" ) )) void StreamCopyAvx2( char* dst, const char* src, std::size_t bytes )
+    {
+        std::size_t head = ( 32 - ( (std::uintptr_t)dst & 31 ) ) & 31;
+        if( head > bytes ) head = bytes;
+        std::memcpy( dst, src, head );
+        dst += head; src += head; bytes -= head;
+        std::size_t i = 0;
+        for( ; i + 128 <= bytes; i += 128 )
+        {
+            const __m256i a = _mm256_loadu_si256( (const __m256i*)( src + i ) ), b = _mm256_loadu_si256( (const __m256i*)( src + i + 32 ) );
+            const __m256i c = _mm256_loadu_si256( (const __m256i*)( src + i + 64 ) ), d = _mm256_loadu_si256( (const __m256i*)( src + i + 96 ) );
+            _mm256_stream_si256( (__m256i*)( dst + i ), a );
+            _mm256_stream_si256( (__m256i*)( dst + i + 32 ), b );
+            _mm256_stream_si256( (__m256i*)( dst + i + 64 ), c );
+            _mm256_stream_si256( (__m256i*)( dst + i + 96 ), d );
+        }
+        _mm_sfence();
+        std::memcpy( dst + i, src + i, bytes - i );
+    }
+#endif
+
+    void CopyToPageable( char* dst, const char* src, std::size_t bytes )
+    {
+#if defined( __x86_64__ )
+        static const bool stream = __builtin_cpu_supports( "avx2" ) && EnvInt( "FASTNOISE2_B200_STREAM_COPY", 1 ) != 0;
+        if( stream && bytes >= 4096 )
+        {
+            StreamCopyAvx2( dst, src, bytes );
+            return;
+        }
+#endif
+        std::memcpy( dst, src, bytes );
+    }
+
     class CopyPool
     {
     public:
@@ -365,7 +406,7 @@ namespace
                 mJobs.push_back( [=, &ticket]
                 {
                     cudaEventSynchronize( ready );
-                    if( end > begin ) std::memcpy( dst + begin, src + begin, end - begin );
+                    if( end > begin ) CopyToPageable( dst + begin, src + begin, end - begin );
                     std::lock_guard<std::mutex> l( ticket.mutex );
                     if( --ticket.pending == 0 ) ticket.done.notify_all();
                 } );
@@ -377,7 +418,7 @@ namespace
         CopyPool()
         {
             int n = EnvInt( "FASTNOISE2_B200_COPY_THREADS", 0 );
-            if( n <= 0 ) n = (int)std::min<unsigned>( 16, std::max<unsigned>( 2, std::thread::hardware_concurrency() / 2 ) );
+            if( n <= 0 ) n = (int)std::min<unsigned>( 16, std::max<unsigned>( 2, std::thread::hardware_concurrency() * 3 / 4 ) ); // 12 of 16 cores measured best (profiles/r2_pageable_probe.txt)
             for( int i = 0; i < n; i++ )
             {
                 mWorkers.emplace_back( [this]
@@ -781,7 +822,10 @@ namespace FastNoise
                 SetLastError( "a single launch is limited to 2^31 - 1 points, and a grid to 2^31 - 1 rows" );
                 return -1;
             }
-            const int ppt = nx % 4u == 0 ? PointsPerThreadFor( points, MaxPointsPerThread() ) : 1;
+            // four points per thread for large calls: groups inside one row when rows are a multiple of four wide, else (uniform
+            // grids at least four wide) four consecutive points of the output with per-point rows
+            int ppt = PointsPerThreadFor( points, MaxPointsPerThread() );
+            if( ppt == 4 && nx % 4u != 0 ) ppt = call.kind != kTileable2D && nx >= 4 && EnvInt( "FASTNOISE2_B200_RAGGED", 1 ) ? kRaggedPointsPerThread : 1;
 
             const Module* m = nullptr;
             Program program;
@@ -789,7 +833,7 @@ namespace FastNoise
             if( program.params.empty() ) program.params.push_back( 0.0f );
 
             int seed = call.seed;
-            const unsigned long long groups = points / (unsigned)ppt;
+            const unsigned long long groups = ppt == kRaggedPointsPerThread ? ( points + 3 ) / 4 : points / (unsigned)ppt;
             if( call.kind == kTileable2D )
             {
                 TileArgsHost a {};
@@ -868,9 +912,10 @@ namespace FastNoise
         int PrepareAll( const Generator* root, int kind )
         {
             // every variant the launchers above can choose
-            for( int ppt : { 4, 1 } )
+            for( int ppt : { 4, 1, kRaggedPointsPerThread } )
             {
-                if( ppt > MaxPointsPerThread() ) continue;
+                if( ppt > 1 && MaxPointsPerThread() < 4 ) continue;
+                if( ppt == kRaggedPointsPerThread && ( kind < kGrid2D || kind > kGrid4D ) ) continue;
                 if( int rc = PrepareOffline( root, kind, ppt ) ) return rc;
             }
             return 0;

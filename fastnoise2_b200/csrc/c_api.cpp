@@ -205,10 +205,13 @@ extern "C"
     int fnb200GetMathMode( void ) { return Impl::MathMode(); }
     unsigned long long fnb200LaunchCount( void ) { return Impl::LaunchCount(); }
 
-    static int DefaultPpt()
+    // which points-per-thread variant fnb200GetKernelSource / fnb200GetKernelParams describe: 4 unless FASTNOISE2_B200_PPT says 1
+    // or 5 (the any-width form of the uniform-grid entries, tests only)
+    static int DefaultPpt( int kind )
     {
         const char* v = std::getenv( "FASTNOISE2_B200_PPT" );
         int p = v && *v ? std::atoi( v ) : 4;
+        if( p == Impl::kRaggedPointsPerThread && kind >= Impl::kGrid2D && kind <= Impl::kGrid4D ) return p;
         return p >= 4 ? 4 : 1;
     }
 
@@ -225,7 +228,7 @@ extern "C"
     long fnb200GetKernelParams( const void* node, int kind, float* buf, long bufCount )
     {
         if( !node || !Impl::EntryKindValid( kind ) ) return FNB200_EINVAL;
-        const std::vector<float> params = Impl::KernelParams( Gen( node ), kind, DefaultPpt() );
+        const std::vector<float> params = Impl::KernelParams( Gen( node ), kind, DefaultPpt( kind ) );
         for( long i = 0; buf && i < bufCount && i < (long)params.size(); i++ ) buf[i] = params[i];
         return (long)params.size();
     }
@@ -233,7 +236,7 @@ extern "C"
     long fnb200GetKernelSource( const void* node, int kind, char* buf, long bufSize )
     {
         if( !node || !Impl::EntryKindValid( kind ) ) return FNB200_EINVAL;
-        std::string source = Impl::KernelSource( Gen( node ), kind, DefaultPpt() );
+        std::string source = Impl::KernelSource( Gen( node ), kind, DefaultPpt( kind ) );
         if( buf && bufSize > 0 )
         {
             long n = std::min<long>( bufSize - 1, (long)source.size() );

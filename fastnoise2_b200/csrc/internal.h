@@ -27,12 +27,15 @@ namespace FastNoise
         };
         inline int EntryDims( int kind ) { return kind == kTileable2D ? 4 : ( kind >= 12 ? kind - 10 : kind ); }
         inline bool EntryKindValid( int kind ) { return ( kind >= 2 && kind <= 5 ) || ( kind >= 12 && kind <= 14 ); }
+        /// "points per thread" code of the uniform-grid entry for rows that are not a multiple of four wide: four consecutive points
+        /// of the row-major output per thread, each with its own row (a group may run over the end of a row)
+        constexpr int kRaggedPointsPerThread = 5;
 
         struct LoweredProgram
         {
             std::string source;  ///< complete CUDA translation unit (device library + generated tree + entry kernel)
             std::string error;   ///< non-empty if the tree cannot be lowered
-            int pointsPerThread; ///< 1 or 4 (only the grid/positions index math depends on it)
+            int pointsPerThread; ///< 1, 4 or kRaggedPointsPerThread (only the grid/positions index math depends on it)
             std::vector<float> params; ///< parameter mode: the values of the kernel's TreeParams argument, in slot order
         };
         /// Generates the CUDA source that evaluates the tree rooted at `root` for one entry kind.

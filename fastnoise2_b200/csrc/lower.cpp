@@ -873,6 +873,81 @@ namespace
         return k.str();
     }
 
+    // Rows of any width with four points per thread (the reference's own consumers generate e.g. 130^3 chunks): a group is four
+    // consecutive points of the row-major output, so it may run over the end of a row -- every point carries its own row, decomposed
+    // with carries instead of divisions. The last group of a call may be partial (its points are clamped and not stored).
+    std::string RaggedGridEntry( int dim, const std::string& root )
+    {
+        std::ostringstream k;
+        k << EntryOpen( "GridArgs", 4, false )
+          << "        const unsigned rowLocal = fn2::fast_div( first, a.divX );\n"
+          << "        const unsigned ix = first - rowLocal * (unsigned)a.count[0];\n"
+          << "        const unsigned row = rowLocal + a.rowBegin;\n";
+        if( dim == 2 )
+        {
+            k << "        const unsigned iy = row;\n";
+        }
+        else if( dim == 3 )
+        {
+            k << "        const unsigned iz = fn2::fast_div( row, a.divY );\n"
+              << "        const unsigned iy = row - iz * (unsigned)a.count[1];\n";
+        }
+        else
+        {
+            k << "        const unsigned plane = fn2::fast_div( row, a.divY );\n"
+              << "        const unsigned iy = row - plane * (unsigned)a.count[1];\n"
+              << "        const unsigned iw = fn2::fast_div( plane, a.divZ );\n"
+              << "        const unsigned iz = plane - iw * (unsigned)a.count[2];\n";
+        }
+        k << "        const unsigned left = a.total - first; // points of this group inside the call (>= 1)\n"
+          << "        float v[4];\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < 4; p++ )\n        {\n"
+          << "            const unsigned q = (unsigned)p < left ? (unsigned)p : left - 1u; // past the end of the call: the last point again\n"
+          << "            unsigned jx = ix + q;\n"
+          << "            unsigned carry = jx >= (unsigned)a.count[0] ? 1u : 0u; // rows are at least four points wide: one carry at most\n"
+          << "            jx -= carry ? (unsigned)a.count[0] : 0u;\n"
+          << "            unsigned jy = iy + carry;\n";
+        if( dim >= 3 )
+        {
+            k << "            carry = jy >= (unsigned)a.count[1] ? 1u : 0u;\n"
+              << "            jy -= carry ? (unsigned)a.count[1] : 0u;\n"
+              << "            unsigned jz = iz + carry;\n";
+        }
+        if( dim == 4 )
+        {
+            k << "            carry = jz >= (unsigned)a.count[2] ? 1u : 0u;\n"
+              << "            jz -= carry ? (unsigned)a.count[2] : 0u;\n"
+              << "            const unsigned jw = iw + carry;\n";
+        }
+        // positions exactly as Generator.inl:160-162: fma( float(index), step, offset )
+        for( int d = 0; d < dim; d++ )
+        {
+            k << "            const F p" << kAxis[d] << " = fn2::fma_( fn2::cvt_f( (int)j" << kAxis[d] << " ), a.step[" << d << "], a.off[" << d << "] );\n";
+        }
+        k << "            v[p] = " << root << "( seed, " << Pos( dim, "p" ) << ", tp );\n"
+          << "        }\n"
+          << "#pragma unroll\n"
+          << "        for( int p = 0; p < 4; p++ )\n        {\n"
+          << "            vmin = fn2::min_( vmin, v[p] );\n"
+          << "            vmax = fn2::max_( vmax, v[p] );\n"
+          << "        }\n"
+          << "        if( live )\n        {\n"
+          << "            if( left >= 4u )\n            {\n"
+          << "                fn2::store_points<4>( out, first, v, a.vecStore != 0 );\n"
+          << "                for( unsigned k = 0; k < a.mirrors; k++ ) fn2::store_points<4>( a.mirror[k], first, v, a.vecStore != 0 );\n"
+          << "            }\n            else\n            {\n"
+          << "                for( unsigned p = 0; p < left; p++ )\n                {\n"
+          << "                    const float value = p == 0 ? v[0] : p == 1 ? v[1] : v[2];\n"
+          << "                    out[first + p] = value;\n"
+          << "                    for( unsigned k = 0; k < a.mirrors; k++ ) a.mirror[k][first + p] = value;\n"
+          << "                }\n            }\n"
+          << "        }\n"
+          << "    }\n"
+          << "    fn2::reduce_minmax( vmin, vmax, any, mm );\n}\n";
+        return k.str();
+    }
+
     std::string GridEntry( int dim, const std::string& root, int ppt )
     {
         std::ostringstream k;
@@ -993,7 +1068,8 @@ namespace FastNoise
         {
             LoweredProgram program;
             program.pointsPerThread = pointsPerThread;
-            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 4 ) )
+            if( !root || !EntryKindValid( entryKind ) || ( pointsPerThread != 1 && pointsPerThread != 4 && pointsPerThread != kRaggedPointsPerThread ) ||
+                ( pointsPerThread == kRaggedPointsPerThread && ( entryKind < kGrid2D || entryKind > kGrid4D ) ) )
             {
                 program.error = "invalid lowering request";
                 return program;
@@ -1018,10 +1094,11 @@ namespace FastNoise
             const char* packEnv = std::getenv( "FASTNOISE2_B200_PACK" );
             const int packMode = packEnv && *packEnv ? std::atoi( packEnv ) : 0;
             const bool pack = packMode >= 2 || ( packMode == 1 && entryDim == 3 );
-            const int width = pointsPerThread >= 2 && pack ? 2 : 1;
+            const bool ragged = pointsPerThread == kRaggedPointsPerThread;
+            const int width = pointsPerThread == 4 && pack ? 2 : 1;
 
             std::ostringstream src;
-            src << "// generated by fastnoise2_b200 -- entry kind " << entryKind << ", " << pointsPerThread << " point(s) per thread, "
+            src << "// generated by fastnoise2_b200 -- entry kind " << entryKind << ", " << ( ragged ? 4 : pointsPerThread ) << " point(s) per thread" << ( ragged ? " (rows of any width), " : ", " )
                 << ( ( mathMode & 1 ) ? "relaxed" : "strict" ) << " math, " << ( ( mathMode & 2 ) ? "generic" : "table" ) << " gradients\n"
                 << "#define FN2_RELAXED " << ( mathMode & 1 ) << "\n"
                 << "#define FN2_TABLES " << ( ( mathMode & 2 ) ? 0 : 1 ) << "\n"
@@ -1044,6 +1121,7 @@ namespace FastNoise
 
             if( entryKind == kTileable2D ) src << TileEntry( rootFn, pointsPerThread );
             else if( entryKind >= kPositions2D ) src << PositionsEntry( dim, rootFn, pointsPerThread );
+            else if( pointsPerThread == kRaggedPointsPerThread ) src << RaggedGridEntry( dim, rootFn );
             else src << GridEntry( dim, rootFn, pointsPerThread );
 
             program.source = src.str();

@@ -147,8 +147,13 @@ def main():
         by_pipe[PIPE.get(op, "other")] += n
         total += n
     import bench
-    ppt = 4  # points per thread of the grid entries at these sizes; printed numbers are per point
-    per_point = lambda n: n / warps / ppt
+    # printed numbers are warp-instructions x 32 per point of the workload = thread-instructions per point with full warps
+    # (a thread walks several 4-point groups, so the warp count alone does not give the point count)
+    import bench
+    points = 1
+    for extent in bench.WORKLOADS[args.workload]["n"]:
+        points *= extent
+    per_point = lambda n: n * 32.0 / points
     print("# %s (%s math): %.1f warp-instructions per point, %d warps, %d unmatched offsets" % (args.workload, args.math, per_point(total), warps, mismatched))
     print("\n## by pipe (instructions per point, share)")
     for k, n in by_pipe.most_common():

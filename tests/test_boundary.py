@@ -148,7 +148,9 @@ print("ok")
     result = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True)
     assert result.returncode == 0 and result.stdout.strip().endswith("ok"), result.stderr[-2000:]
     cubins = glob.glob(str(tmp_path / "*.cubin"))
-    assert len(cubins) == 8  # per tree: the 4-points-per-thread kernel (two points per value) and the 1-point one (one point per value)
+    # per tree (all four are uniform-grid kinds): the 4-points-per-thread kernel (two points per value), the 1-point one and the
+    # any-row-width one (one point per value each)
+    assert len(cubins) == 12
     packed = 0
     for cubin in cubins:
         sass = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout

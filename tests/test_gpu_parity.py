@@ -490,3 +490,69 @@ def test_packed_path_every_node_and_random_trees(gpu, ref, force_packed):
             if not same(a.tileable2d(40, 24, 1.3, 0.9, index)[0], b.tileable2d(40, 24, 1.3, 0.9, index)[0]):
                 failures.append((index, "tileable2d", text))
     assert not failures, failures[:5]
+
+
+@pytest.fixture
+def force_large_call_path():
+    """Small test grids normally run one point per thread; FASTNOISE2_B200_FILL=0 makes them take the code path of large calls."""
+    saved = os.environ.get("FASTNOISE2_B200_FILL")
+    os.environ["FASTNOISE2_B200_FILL"] = "0"
+    yield
+    if saved is None:
+        os.environ.pop("FASTNOISE2_B200_FILL", None)
+    else:
+        os.environ["FASTNOISE2_B200_FILL"] = saved
+
+
+def test_any_width_rows_keep_four_points_per_thread(gpu, ref, force_large_call_path):
+    """Rows whose width 4 does not divide (the reference's own consumers generate (128+2)^3 chunks,
+    tools/NodeEditor/MeshNoisePreview.h:157) run four consecutive output points per thread, groups straddling row / plane / volume
+    ends, partial last group: bit-identical to the oracle in 2D, 3D and 4D, whole calls and row slabs."""
+    launches = gpu.lib.fnb200LaunchCount()
+    for name in ("c4_terrain", "c2_fbm5_perlin"):
+        a, b = helpers.ProductNode(gpu, gpu.TREES[name]), helpers.RefNode(ref, gpu.TREES[name])
+        for n in [(5, 3, 2), (7, 9, 3), (130, 5, 3), (33, 2, 2), (6, 1, 1), (9, 1, 5)]:
+            got, gmm = a.grid3d(0.5, -0.25, 3.0, *n, 0.11, 0.13, 0.17, 1337)
+            want, wmm = b.grid3d(0.5, -0.25, 3.0, *n, 0.11, 0.13, 0.17, 1337)
+            assert np.array_equal(bits(got), bits(want)), (name, n)
+            assert tuple(gmm) == tuple(wmm)
+        for n in [(5, 1), (7, 9), (131, 17), (6, 5)]:
+            got, gmm = a.grid2d(-3.0, 2.0, *n, 0.09, 0.07, 5)
+            want, wmm = b.grid2d(-3.0, 2.0, *n, 0.09, 0.07, 5)
+            assert np.array_equal(bits(got), bits(want)), (name, n)
+            assert tuple(gmm) == tuple(wmm)
+        for n in [(5, 3, 2, 2), (7, 2, 3, 2), (9, 1, 1, 3)]:
+            got, gmm = a.grid4d(0.0, 1.0, 2.0, 3.0, *n, 0.19, 0.17, 0.13, 0.11, 5)
+            want, wmm = b.grid4d(0.0, 1.0, 2.0, 3.0, *n, 0.19, 0.17, 0.13, 0.11, 5)
+            assert np.array_equal(bits(got), bits(want)), (name, n)
+            assert tuple(gmm) == tuple(wmm)
+    # several staging chunks (each starts at its own row of the grid) and a device-resident destination
+    os.environ["FASTNOISE2_B200_STAGING_MB"] = "1"
+    try:
+        a, b = helpers.ProductNode(gpu, gpu.TREES["c1_simplex"]), helpers.RefNode(ref, gpu.TREES["c1_simplex"])
+        got, gmm = a.grid3d(0.5, -0.25, 3.0, 130, 70, 61, 0.11, 0.13, 0.17, 7)
+        want, wmm = b.grid3d(0.5, -0.25, 3.0, 130, 70, 61, 0.11, 0.13, 0.17, 7)
+        assert np.array_equal(bits(got), bits(want)) and tuple(gmm) == tuple(wmm)
+    finally:
+        os.environ.pop("FASTNOISE2_B200_STAGING_MB", None)
+    import torch
+    dev = torch.empty(130 * 70 * 61, dtype=torch.float32, device="cuda")
+    mm = gpu.Generator(gpu.TREES["c1_simplex"]).grid3d(dev, 0.5, -0.25, 3.0, 130, 70, 61, 0.11, 0.13, 0.17, 7)
+    assert np.array_equal(bits(dev.cpu().numpy()), bits(want)) and tuple(mm) == tuple(wmm)
+    assert gpu.lib.fnb200LaunchCount() > launches
+    # the any-width entry is what ran: its text is what fnb200GetKernelSource returns under FASTNOISE2_B200_PPT=5
+    os.environ["FASTNOISE2_B200_PPT"] = "5"
+    try:
+        assert "rows of any width" in gpu.Generator(gpu.TREES["c4_terrain"]).kernel_source(3)
+    finally:
+        os.environ.pop("FASTNOISE2_B200_PPT", None)
+
+
+def test_chunk_sized_odd_width_call_at_full_size(gpu, ref):
+    """130^3 (a mesh-preview chunk with its one-voxel apron) is large enough to take the four-point path on its own."""
+    tree = gpu.TREES["c4_terrain"]
+    a, b = helpers.ProductNode(gpu, tree), helpers.RefNode(ref, tree)
+    got, gmm = a.grid3d(-65.0, -65.0, -65.0, 130, 130, 130, 1.0, 1.0, 1.0, 1337)
+    want, wmm = b.grid3d(-65.0, -65.0, -65.0, 130, 130, 130, 1.0, 1.0, 1.0, 1337)
+    assert np.array_equal(bits(got), bits(want))
+    assert tuple(gmm) == tuple(wmm)

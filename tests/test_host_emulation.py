@@ -314,16 +314,37 @@ def test_smaller_points_per_thread_variants_on_host(fn, ref, tmp_path, monkeypat
     """The 1-point-per-thread variant (what the library launches for row widths that 4 does not divide, and for calls too small
     to fill the GPU) on odd grid sizes, and the literal-parameter form of the kernels (FASTNOISE2_B200_LITERALS=1)."""
     failures = []
-    for ppt, literals, n in (("1", "0", (9, 7, 5)), ("1", "1", (10, 7, 3)), ("4", "1", (12, 7, 3))):
+    # "5" = four points per thread over rows of ANY width (groups run over row ends; 9 x 7 x 5 = 315 points leaves a partial last group)
+    for ppt, literals, n in (("1", "0", (9, 7, 5)), ("1", "1", (10, 7, 3)), ("4", "1", (12, 7, 3)), ("5", "0", (9, 7, 5)), ("5", "0", (5, 3, 2))):
         monkeypatch.setenv("FASTNOISE2_B200_PPT", ppt)
         monkeypatch.setenv("FASTNOISE2_B200_LITERALS", literals)
         for name in ("c4_terrain", "c3a_cellular_distance"):
             lib, (got_ppt, params) = build_on_host(fn, fn.TREES[name], 3, str(tmp_path), "ppt")
-            assert got_ppt == int(ppt) and (len(params) > 1) == (literals == "0")
+            assert got_ppt == (4 if ppt == "5" else int(ppt)) and (len(params) > 1) == (literals == "0")
             out = np.zeros(int(np.prod(n)), np.float32)
             lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), 3, (ctypes.c_float * 3)(0.5, -2.0, 3.0), (ctypes.c_int * 3)(*n),
                               (ctypes.c_float * 3)(1.3, 1.1, 0.9), 7, got_ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
             want = helpers.RefNode(ref, fn.TREES[name]).grid3d(0.5, -2.0, 3.0, *n, 1.3, 1.1, 0.9, 7)[0]
             if not same(out, want):
                 failures.append((ppt, name, helpers.compare(out, want)))
+    assert not failures, failures
+
+
+def test_any_width_four_point_groups_on_host(fn, ref, tmp_path, monkeypatch):
+    """Four points per thread over rows whose width 4 does not divide (FASTNOISE2_B200_PPT=5 selects that entry form for
+    fnb200GetKernelSource): groups straddle row, plane and volume ends; the last group of a call is partial. 2D, 3D and 4D."""
+    monkeypatch.setenv("FASTNOISE2_B200_PPT", "5")
+    text = fn.TREES["c2_fbm5_perlin"]
+    node = helpers.RefNode(ref, text)
+    failures = []
+    for dims, n in ((2, (7, 9)), (2, (5, 3)), (3, (6, 5, 3)), (3, (13, 3, 3)), (4, (5, 3, 2, 3)), (4, (7, 2, 3, 2))):
+        lib, (ppt, params) = build_on_host(fn, text, dims, str(tmp_path), "ragged%d" % dims)
+        assert ppt == 4
+        off, step = (0.5, -2.0, 3.0, 7.5)[:dims], (0.13, 0.11, 0.09, 0.21)[:dims]
+        out = np.zeros(int(np.prod(n)), np.float32)
+        lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), dims, (ctypes.c_float * dims)(*off), (ctypes.c_int * dims)(*n),
+                          (ctypes.c_float * dims)(*step), 11, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
+        want = getattr(node, "grid%dd" % dims)(*off, *n, *step, 11)[0]
+        if not same(out, want):
+            failures.append((dims, n, helpers.compare(out, want)))
     assert not failures, failures
