@@ -13,5 +13,5 @@ python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_referen
 python bench.py > gpurun_out/bench_default_${tag}.json 2> gpurun_out/bench_default_${tag}.err
 python tools/pageable_probe.py --nz 512 --calls 3 > gpurun_out/pageable_probe_${tag}.txt 2>&1
 python tools/call_latency.py > gpurun_out/call_latency_${tag}.txt 2>&1
-python tools/ab_sweep.py --workloads c4 --variants "w130:" > /dev/null 2>&1
+python tools/odd_width.py > gpurun_out/odd_width_${tag}.txt 2>&1
 tail -c 400 gpurun_out/bench_default_${tag}.json
