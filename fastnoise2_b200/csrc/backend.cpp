@@ -825,11 +825,20 @@ namespace FastNoise
             // four points per thread for large calls: groups inside one row when rows are a multiple of four wide, else (uniform
             // grids at least four wide) four consecutive points of the output with per-point rows
             int ppt = PointsPerThreadFor( points, MaxPointsPerThread() );
-            if( ppt == 4 && nx % 4u != 0 ) ppt = call.kind != kTileable2D && nx >= 4 && EnvInt( "FASTNOISE2_B200_RAGGED", 1 ) ? kRaggedPointsPerThread : 1;
+            const int ragged = EnvInt( "FASTNOISE2_B200_RAGGED", 1 ); // 0: never, 1: by code size (below), 2: always
+            if( ppt == 4 && nx % 4u != 0 ) ppt = call.kind != kTileable2D && nx >= 4 && ragged ? kRaggedPointsPerThread : 1;
 
             const Module* m = nullptr;
             Program program;
             if( int rc = ModuleFor( root, call.kind, ppt, m, program ) ) return rc;
+            if( ppt == kRaggedPointsPerThread && ragged == 1 && m->codeBytes > kConvergedCodeBytes )
+            {
+                // Heavy trees: four inlined copies of the tree with per-point rows lose to the one-point kernel, whose code fits
+                // the instruction cache (terrain tree 1030 x 1030 x 250: 13.8 vs 13.4 ms; light trees gain 5-19 % from the
+                // four-point form, profiles/r2_odd_width.txt)
+                ppt = 1;
+                if( int rc = ModuleFor( root, call.kind, ppt, m, program ) ) return rc;
+            }
             if( program.params.empty() ) program.params.push_back( 0.0f );
 
             int seed = call.seed;

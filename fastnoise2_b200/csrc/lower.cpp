@@ -873,7 +873,8 @@ namespace
         return k.str();
     }
 
-    // Rows of any width with four points per thread (the reference's own consumers generate e.g. 130^3 chunks): a group is four
+    // Rows of any width with four points per thread (chunk sizes such as the reference mesh preview's (128+2)^3,
+    // tools/NodeEditor/MeshNoisePreview.cpp:446, as uniform grids): a group is four
     // consecutive points of the row-major output, so it may run over the end of a row -- every point carries its own row, decomposed
     // with carries instead of divisions. The last group of a call may be partial (its points are clamped and not stored).
     std::string RaggedGridEntry( int dim, const std::string& root )

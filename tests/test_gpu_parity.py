@@ -494,19 +494,22 @@ def test_packed_path_every_node_and_random_trees(gpu, ref, force_packed):
 
 @pytest.fixture
 def force_large_call_path():
-    """Small test grids normally run one point per thread; FASTNOISE2_B200_FILL=0 makes them take the code path of large calls."""
-    saved = os.environ.get("FASTNOISE2_B200_FILL")
+    """Small test grids normally run one point per thread; FASTNOISE2_B200_FILL=0 makes them take the code path of large calls,
+    FASTNOISE2_B200_RAGGED=2 keeps the any-width four-point form for heavy trees too (production picks it by code size)."""
+    saved = {k: os.environ.get(k) for k in ("FASTNOISE2_B200_FILL", "FASTNOISE2_B200_RAGGED")}
     os.environ["FASTNOISE2_B200_FILL"] = "0"
+    os.environ["FASTNOISE2_B200_RAGGED"] = "2"
     yield
-    if saved is None:
-        os.environ.pop("FASTNOISE2_B200_FILL", None)
-    else:
-        os.environ["FASTNOISE2_B200_FILL"] = saved
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def test_any_width_rows_keep_four_points_per_thread(gpu, ref, force_large_call_path):
-    """Rows whose width 4 does not divide (the reference's own consumers generate (128+2)^3 chunks,
-    tools/NodeEditor/MeshNoisePreview.h:157) run four consecutive output points per thread, groups straddling row / plane / volume
+    """Rows whose width 4 does not divide (chunk sizes such as the (128+2)^3 of tools/NodeEditor/MeshNoisePreview.cpp:446 as
+    uniform grids) run four consecutive output points per thread, groups straddling row / plane / volume
     ends, partial last group: bit-identical to the oracle in 2D, 3D and 4D, whole calls and row slabs."""
     launches = gpu.lib.fnb200LaunchCount()
     for name in ("c4_terrain", "c2_fbm5_perlin"):

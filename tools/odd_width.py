@@ -1,5 +1,6 @@
-"""Device-resident throughput on grids whose row width 4 does not divide: four points per thread over any width (default)
-against one point per thread (FASTNOISE2_B200_RAGGED=0, what such grids ran before), plus the nearest multiple-of-4 width.
+"""Device-resident throughput on grids whose row width 4 does not divide: four points per thread over any width (forced,
+FASTNOISE2_B200_RAGGED=2), the library's own choice (1: that form unless the kernel is above 48 KB of code), one point per
+thread (0, what such grids ran before), and the nearest multiple-of-4 width.
 
     python tools/odd_width.py
 """
@@ -20,7 +21,7 @@ def main():
              ("c3a_cellular_distance", 3, (1030, 1030, 250)), ("c2_fbm5_perlin", 2, (16390, 16390))]
     for tree, dims, n in cases:
         g = fn.Generator(fn.TREES[tree])
-        for label, shape, ragged in (("any-width x4", n, "1"), ("1 per thread", n, "0"), ("width % 4 == 0", (n[0] - n[0] % 4,) + n[1:], "1")):
+        for label, shape, ragged in (("any-width x4", n, "2"), ("library's choice", n, "1"), ("1 per thread", n, "0"), ("width % 4 == 0", (n[0] - n[0] % 4,) + n[1:], "1")):
             os.environ["FASTNOISE2_B200_RAGGED"] = ragged
             points = 1
             for e in shape:
