@@ -354,11 +354,14 @@ namespace
     }
 #endif
 
-    void CopyToPageable( char* dst, const char* src, std::size_t bytes )
+    // `streaming`: the chunk this slice belongs to is too large to stay in the last-level cache anyway. Small destinations (a
+    // 128^3 chunk is 8 MB) are copied with plain stores: they are usually cache-resident -- the caller reads them next -- and
+    // non-temporal stores to cached lines are slower (128^3 pageable: 855 us streamed, 435 us plain; profiles/r2_call_latency.txt)
+    void CopyToPageable( char* dst, const char* src, std::size_t bytes, bool streaming )
     {
 #if defined( __x86_64__ )
         static const bool stream = __builtin_cpu_supports( "avx2" ) && EnvInt( "FASTNOISE2_B200_STREAM_COPY", 1 ) != 0;
-        if( stream && bytes >= 4096 )
+        if( stream && streaming && bytes >= 4096 )
         {
             StreamCopyAvx2( dst, src, bytes );
             return;
@@ -394,6 +397,7 @@ namespace
         void Submit( cudaEvent_t ready, const char* src, char* dst, std::size_t bytes, Ticket& ticket )
         {
             const int parts = (int)std::max<std::size_t>( 1, std::min<std::size_t>( mWorkers.size(), bytes / ( 1u << 20 ) ) );
+            const bool streaming = bytes >= ( 32u << 20 );
             {
                 std::lock_guard<std::mutex> lock( ticket.mutex );
                 ticket.pending += parts;
@@ -406,7 +410,7 @@ namespace
                 mJobs.push_back( [=, &ticket]
                 {
                     cudaEventSynchronize( ready );
-                    if( end > begin ) CopyToPageable( dst + begin, src + begin, end - begin );
+                    if( end > begin ) CopyToPageable( dst + begin, src + begin, end - begin, streaming );
                     std::lock_guard<std::mutex> l( ticket.mutex );
                     if( --ticket.pending == 0 ) ticket.done.notify_all();
                 } );

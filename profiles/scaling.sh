@@ -4,7 +4,7 @@
 tag=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_${tag}.txt 2>&1
-for n in 8 4; do
+for n in 8 4 2; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 --extras \
       > gpurun_out/scale_n${n}_${tag}.json 2> gpurun_out/scale_n${n}_${tag}.err
 done
