@@ -147,54 +147,57 @@ namespace fn2
             stemB = fb - (float)( kDistanceSquaredB * 0.5 );
             v[0] = { hash_hbs<SCALE>( seed, xP, yP, zP ), dxB, dyB, dzB, sq2( fb ) };
         }
+        // The reference flips signs with an XOR mask (`c ^ sign`, `d ^ sign`). A flipped constant or coordinate is the value times
+        // s = -1 or +1, and that product is exact, so every `a - ( c ^ sign )` is ONE fused operation fnma_( c, s, a ) with the
+        // same single rounding, and `fma( c ^ sign, coordSum, stem )` is fma( c, coordSum * s, stem ): the sign work moves from
+        // the half-rate ALU pipe (SEL + LOP3 per use) to the FMA pipe and the XORs disappear. Stepped lattice coordinates
+        // (base +- prime by the same mask) are selected from the two neighbours computed once per axis.
+        const I xPp = iadd( xP, kPX ), yPp = iadd( yP, kPY ), zPp = iadd( zP, kPZ );
+        const I xPm = isub( xP, kPX ), yPm = isub( yP, kPY ), zPm = isub( zP, kPZ );
         { // <1,1,1> or <-1,-1,-1>
             B sm = xyzN < 0.0f;
-            I sign = signbit_if( sm );
-            F o = fxor( (float)( 3 * kReflectUnskew3 + 1 ), sign );
-            F fb = max_( fma_( o, coordSum, stemA ), 0.0f );
-            v[1] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o, dyB - o, dzB - o, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            constexpr float o = (float)( 3 * kReflectUnskew3 + 1 );
+            F fb = max_( fma_( F( o ), coordSum * s, stemA ), 0.0f );
+            v[1] = { hash_hbs<SCALE>( seed, select( sm, xPm, xPp ), select( sm, yPm, yPp ), select( sm, zPm, zPp ) ), fnma_( F( o ), s, dxB ), fnma_( F( o ), s, dyB ), fnma_( F( o ), s, dzB ), sq2( fb ) };
         }
+        constexpr float o2 = (float)( 2 * kReflectUnskew3 );
         { // <1,1,0> or <-1,-1,0>
             B sm = xyzN < zN;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            F fb = min_( fxor( dzB, sign ) - stemB, 0.0f );
-            v[2] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), step_prime( yP, kPY, sm ), zP ), dxB, dyB, dzB - o0, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = min_( fms_( dzB, s, stemB ), 0.0f );
+            v[2] = { hash_hbs<SCALE>( seed, select( sm, xPm, xPp ), select( sm, yPm, yPp ), zP ), dxB, dyB, fnma_( F( o2 ), s, dzB ), sq2( fb ) };
         }
         { // <1,0,1> or <-1,0,-1>
             B sm = xyzN < yN;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            F fb = min_( fxor( dyB, sign ) - stemB, 0.0f );
-            v[3] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), yP, step_prime( zP, kPZ, sm ) ), dxB, dyB - o0, dzB, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = min_( fms_( dyB, s, stemB ), 0.0f );
+            v[3] = { hash_hbs<SCALE>( seed, select( sm, xPm, xPp ), yP, select( sm, zPm, zPp ) ), dxB, fnma_( F( o2 ), s, dyB ), dzB, sq2( fb ) };
         }
         { // <0,1,1> or <0,-1,-1>
             B sm = xyzN < xN;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)( 2 * kReflectUnskew3 ), sign );
-            F fb = min_( fxor( dxB, sign ) - stemB, 0.0f );
-            v[4] = { hash_hbs<SCALE>( seed, xP, step_prime( yP, kPY, sm ), step_prime( zP, kPZ, sm ) ), dxB - o0, dyB, dzB, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = min_( fms_( dxB, s, stemB ), 0.0f );
+            v[4] = { hash_hbs<SCALE>( seed, xP, select( sm, yPm, yPp ), select( sm, zPm, zPp ) ), fnma_( F( o2 ), s, dxB ), dyB, dzB, sq2( fb ) };
         }
+        constexpr float o1 = (float)kReflectUnskew3;
         { // <1,0,0> or <-1,0,0>
             B sm = xN < 0.0f;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)kReflectUnskew3, sign );
-            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dxB, sign ), 0.0f );
-            v[5] = { hash_hbs<SCALE>( seed, step_prime( xP, kPX, sm ), yP, zP ), dxB + o0, dyB - o0, dzB - o0, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = max_( fma_( dxB, s, fma_( F( o1 ), coordSum * s, stemA ) ), 0.0f );
+            v[5] = { hash_hbs<SCALE>( seed, select( sm, xPm, xPp ), yP, zP ), fma_( F( o1 ), s, dxB ), fnma_( F( o1 ), s, dyB ), fnma_( F( o1 ), s, dzB ), sq2( fb ) };
         }
         { // <0,1,0> or <0,-1,0>
             B sm = yN < 0.0f;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)kReflectUnskew3, sign );
-            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dyB, sign ), 0.0f );
-            v[6] = { hash_hbs<SCALE>( seed, xP, step_prime( yP, kPY, sm ), zP ), dxB - o0, dyB + o0, dzB - o0, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = max_( fma_( dyB, s, fma_( F( o1 ), coordSum * s, stemA ) ), 0.0f );
+            v[6] = { hash_hbs<SCALE>( seed, xP, select( sm, yPm, yPp ), zP ), fnma_( F( o1 ), s, dxB ), fma_( F( o1 ), s, dyB ), fnma_( F( o1 ), s, dzB ), sq2( fb ) };
         }
         { // <0,0,1> or <0,0,-1>
             B sm = zN < 0.0f;
-            I sign = signbit_if( sm );
-            F o0 = fxor( (float)kReflectUnskew3, sign );
-            F fb = max_( fma_( o0, coordSum, stemA ) + fxor( dzB, sign ), 0.0f );
-            v[7] = { hash_hbs<SCALE>( seed, xP, yP, step_prime( zP, kPZ, sm ) ), dxB - o0, dyB - o0, dzB + o0, sq2( fb ) };
+            F s = select( sm, F( -1.0f ), F( 1.0f ) );
+            F fb = max_( fma_( dzB, s, fma_( F( o1 ), coordSum * s, stemA ) ), 0.0f );
+            v[7] = { hash_hbs<SCALE>( seed, xP, yP, select( sm, zPm, zPp ) ), fnma_( F( o1 ), s, dxB ), fnma_( F( o1 ), s, dyB ), fma_( F( o1 ), s, dzB ), sq2( fb ) };
         }
     }
 
@@ -287,37 +290,38 @@ namespace fn2
             v[0] = { hash_hbs<SCALE>( seed, xP, yP, zP, wP ), dxB, dyB, dzB, dwB, sq2( fb ) };
         }
 
-        // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many.
-        // Coordinates on stepping axes use offset1 = (K*u + 1)^sign, the others offset0 = (K*u)^sign. FALLOFF is
-        // the vertex-class specific falloff base expression [Simplex.inl:692-931].
-#define FN2_SS4_VERTEX( SLOT, COND, MX, MY, MZ, MW, K, FALLOFF ) \
+        // One lattice vertex: MX..MW say which axes step (by +-1 according to the sign mask), K is how many. Coordinates on stepping
+        // axes use offset1 = (K*u + 1)^sign, the others offset0 = (K*u)^sign [Simplex.inl:692-931]. As in 3D above the sign mask is
+        // applied as the exact factor s = -1 / +1 inside fused operations: OFF picks the offset that multiplies coordSum, STEM the
+        // falloff stem, FALLOFF finishes the vertex-class specific falloff base from `base` and `s`.
+        const I xPp = iadd( xP, kPX ), yPp = iadd( yP, kPY ), zPp = iadd( zP, kPZ ), wPp = iadd( wP, kPW );
+        const I xPm = isub( xP, kPX ), yPm = isub( yP, kPY ), zPm = isub( zP, kPZ ), wPm = isub( wP, kPW );
+#define FN2_SS4_VERTEX( SLOT, COND, MX, MY, MZ, MW, K, OFF, STEM, FALLOFF ) \
         { \
             B sm = COND; \
-            I sign = signbit_if( sm ); \
-            F o1 = fxor( (float)( K * kUnskew4 + 1 ), sign ); \
-            F o0 = fxor( (float)( K * kUnskew4 ), sign ); \
-            (void)o0; \
+            F s = select( sm, F( -1.0f ), F( 1.0f ) ); \
+            F base = fma_( F( (float)( K * kUnskew4 + OFF ) ), coordSum * s, STEM ); \
             F fb = max_( FALLOFF, 0.0f ); \
-            v[SLOT] = { hash_hbs<SCALE>( seed, select( MX, step_prime( xP, kPX, sm ), xP ), select( MY, step_prime( yP, kPY, sm ), yP ), select( \
-                                     MZ, step_prime( zP, kPZ, sm ), zP ), select( MW, step_prime( wP, kPW, sm ), wP )), \
-                        dxB - ( select( MX, o1, o0 )), dyB - ( select( MY, o1, o0 )), dzB - ( select( MZ, o1, o0 )), dwB - ( select( MW, o1, o0 )), sq2( fb ) }; \
+            v[SLOT] = { hash_hbs<SCALE>( seed, MX ? select( sm, xPm, xPp ) : xP, MY ? select( sm, yPm, yPp ) : yP, MZ ? select( sm, zPm, zPp ) : zP, MW ? select( sm, wPm, wPp ) : wP ), \
+                        fnma_( F( (float)( K * kUnskew4 + MX ) ), s, dxB ), fnma_( F( (float)( K * kUnskew4 + MY ) ), s, dyB ), \
+                        fnma_( F( (float)( K * kUnskew4 + MZ ) ), s, dzB ), fnma_( F( (float)( K * kUnskew4 + MW ) ), s, dwB ), sq2( fb ) }; \
         }
 
-        FN2_SS4_VERTEX( 1, xyzwN < 0.0f, 1, 1, 1, 1, 4, fma_( o1, coordSum, stemA ) )
-        FN2_SS4_VERTEX( 2, xyzwN < wN, 1, 1, 1, 0, 3, fma_( o1, coordSum, stemB ) - fxor( dwB, sign ) )
-        FN2_SS4_VERTEX( 3, xyzwN < zN, 1, 1, 0, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dzB, sign ) )
-        FN2_SS4_VERTEX( 4, xyzwN < yN, 1, 0, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dyB, sign ) )
-        FN2_SS4_VERTEX( 5, xyzwN < xN, 0, 1, 1, 1, 3, fma_( o1, coordSum, stemB ) - fxor( dxB, sign ) )
-        FN2_SS4_VERTEX( 6, xN < 0.0f, 1, 0, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dxB, sign ) )
-        FN2_SS4_VERTEX( 7, xN < -yN, 1, 1, 0, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dyB, sign ) )
-        FN2_SS4_VERTEX( 8, xN < -zN, 1, 0, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dzB, sign ) )
-        FN2_SS4_VERTEX( 9, xN < -wN, 1, 0, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dxB + dwB, sign ) )
-        FN2_SS4_VERTEX( 10, yN < 0.0f, 0, 1, 0, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dyB, sign ) )
-        FN2_SS4_VERTEX( 11, yN < -zN, 0, 1, 1, 0, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dzB, sign ) )
-        FN2_SS4_VERTEX( 12, yN < -wN, 0, 1, 0, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dyB + dwB, sign ) )
-        FN2_SS4_VERTEX( 13, zN < 0.0f, 0, 0, 1, 0, 1, fma_( o0, coordSum, stemA ) + fxor( dzB, sign ) )
-        FN2_SS4_VERTEX( 14, zN < -wN, 0, 0, 1, 1, 2, fma_( o0, coordSum, stemB ) + fxor( dzB + dwB, sign ) )
-        FN2_SS4_VERTEX( 15, wN < 0.0f, 0, 0, 0, 1, 1, fma_( o0, coordSum, stemA ) + fxor( dwB, sign ) )
+        FN2_SS4_VERTEX( 1, xyzwN < 0.0f, 1, 1, 1, 1, 4, 1, stemA, base )
+        FN2_SS4_VERTEX( 2, xyzwN < wN, 1, 1, 1, 0, 3, 1, stemB, fnma_( dwB, s, base ) )
+        FN2_SS4_VERTEX( 3, xyzwN < zN, 1, 1, 0, 1, 3, 1, stemB, fnma_( dzB, s, base ) )
+        FN2_SS4_VERTEX( 4, xyzwN < yN, 1, 0, 1, 1, 3, 1, stemB, fnma_( dyB, s, base ) )
+        FN2_SS4_VERTEX( 5, xyzwN < xN, 0, 1, 1, 1, 3, 1, stemB, fnma_( dxB, s, base ) )
+        FN2_SS4_VERTEX( 6, xN < 0.0f, 1, 0, 0, 0, 1, 0, stemA, fma_( dxB, s, base ) )
+        FN2_SS4_VERTEX( 7, xN < -yN, 1, 1, 0, 0, 2, 0, stemB, fma_( dxB + dyB, s, base ) )
+        FN2_SS4_VERTEX( 8, xN < -zN, 1, 0, 1, 0, 2, 0, stemB, fma_( dxB + dzB, s, base ) )
+        FN2_SS4_VERTEX( 9, xN < -wN, 1, 0, 0, 1, 2, 0, stemB, fma_( dxB + dwB, s, base ) )
+        FN2_SS4_VERTEX( 10, yN < 0.0f, 0, 1, 0, 0, 1, 0, stemA, fma_( dyB, s, base ) )
+        FN2_SS4_VERTEX( 11, yN < -zN, 0, 1, 1, 0, 2, 0, stemB, fma_( dyB + dzB, s, base ) )
+        FN2_SS4_VERTEX( 12, yN < -wN, 0, 1, 0, 1, 2, 0, stemB, fma_( dyB + dwB, s, base ) )
+        FN2_SS4_VERTEX( 13, zN < 0.0f, 0, 0, 1, 0, 1, 0, stemA, fma_( dzB, s, base ) )
+        FN2_SS4_VERTEX( 14, zN < -wN, 0, 0, 1, 1, 2, 0, stemB, fma_( dzB + dwB, s, base ) )
+        FN2_SS4_VERTEX( 15, wN < 0.0f, 0, 0, 0, 1, 1, 0, stemA, fma_( dwB, s, base ) )
 #undef FN2_SS4_VERTEX
     }
 
