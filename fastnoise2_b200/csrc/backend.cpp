@@ -925,8 +925,10 @@ namespace FastNoise
         int PrepareAll( const Generator* root, int kind )
         {
             // every variant the launchers above can choose
+            const int only = EnvInt( "FASTNOISE2_B200_PREPARE_ONLY", 0 ); // tools: compile one points-per-thread form (4, 1 or 5)
             for( int ppt : { 4, 1, kRaggedPointsPerThread } )
             {
+                if( only && ppt != only ) continue;
                 if( ppt > 1 && MaxPointsPerThread() < 4 ) continue;
                 if( ppt == kRaggedPointsPerThread && ( kind < kGrid2D || kind > kGrid4D ) ) continue;
                 if( int rc = PrepareOffline( root, kind, ppt ) ) return rc;

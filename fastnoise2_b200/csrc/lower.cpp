@@ -826,7 +826,9 @@ namespace
     // once per thread, not once per group. A group is `ppt` consecutive points of one x-row (4: rows are a multiple of 4 wide and
     // the thread stores one 16-byte vector; 1: any width, a warp stores 32 consecutive floats), evaluated FN2_W at a time
     // (FN2_W = 2: one fpair per two points, see fn2_device_pack.cuh).
-    const char* const kEntryHead = "( float* __restrict__ out, const fn2::";
+    // (the argument struct is __grid_constant__ too: its peer-pointer array is indexed at run time, and without the qualifier the
+    // tileable entry copied the whole struct to local memory at the top of every thread)
+    const char* const kEntryHead = "( float* __restrict__ out, const FN2_GRID_CONSTANT fn2::";
     std::string EntryOpen( const char* argsType, int ppt, bool wide )
     {
         std::ostringstream k;

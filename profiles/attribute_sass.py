@@ -41,6 +41,8 @@ def build_cubin(workload, math):
     import bench
     cache = tempfile.mkdtemp(prefix="fn2_attr_")
     os.environ["FASTNOISE2_B200_CACHE"] = cache
+    # fnb200Prepare compiles every points-per-thread form the launcher can choose; large calls (what ncu captured) run the 4-point one
+    os.environ["FASTNOISE2_B200_PREPARE_ONLY"] = "4"
     import fastnoise2_b200 as fn
     from fastnoise2_b200 import api
     fn.set_math_mode(bench.MATH_MODES[math])
@@ -51,10 +53,8 @@ def build_cubin(workload, math):
     g.prepare(kind)
     source = g.kernel_source(kind)
     cubins = glob.glob(os.path.join(cache, "*.cubin"))
-    assert cubins, cache
-    # fnb200Prepare compiles every points-per-thread variant the launcher can choose; large calls (what ncu captured) run the
-    # 4-point one, which is the larger cubin
-    return max(cubins, key=os.path.getsize), source, cache
+    assert len(cubins) == 1, cubins
+    return cubins[0], source, cache
 
 
 def function_table(text):
