@@ -168,9 +168,13 @@ def run_cpu(lib, w, shape, threads):
         sec = lib.fn2refTimedGridMT(node.handle, out.ctypes.data, 2, nx, ny, 1, 0.0, 0.0, 0.0, w["step"], SEED, threads, None)
         return sec, out.size, min(threads, ny)
     if w["kind"] == "tileable2d":
-        # GenTileable2D has no slab form in the reference API (the torus mapping needs the whole tile size): ONE thread, stated in `cores`
+        # GenTileable2D has no slab form in the reference API (it walks the whole image): the threaded driver splits the rows and
+        # evaluates each slab through the reference's GenPositionArray4D over the torus positions (oracle/ref/ref_extra.cpp)
         nx, ny = shape
         out = np.empty(nx * ny, np.float32)
+        if hasattr(lib, "fn2refTimedTileableMT") and threads > 1:
+            sec = lib.fn2refTimedTileableMT(node.handle, out.ctypes.data, nx, ny, w["step"], w["step"], SEED, threads, None)
+            return sec, out.size, min(threads, ny)
         t0 = time.time()
         lib.fnGenTileable2D(node.handle, out.ctypes.data, nx, ny, w["step"], w["step"], SEED, None)
         return time.time() - t0, out.size, 1
@@ -206,7 +210,7 @@ def cpu_baseline(w, target_seconds):
     sec, pts = best
     return {"value": pts / sec / 1e6, "unit": "Mpoints/s", "cores": used, "kind": "reference",
             "sample": "oracle/_ref %s (reference node sources over the FastSIMD stand-in, reference default flags), %s of the workload grid = %d points in %.2f s, %d thread(s)%s" % (
-                variant, "x".join(str(s) for s in shape), pts, sec, used, ", one slab per thread" if used > 1 else " (the reference API has no slab form of this call)"),
+                variant, "x".join(str(s) for s in shape), pts, sec, used, (", rows split over the threads through the reference's GenPositionArray4D on the torus positions (GenTileable2D has no slab form)" if w["kind"] == "tileable2d" else ", one slab per thread") if used > 1 else " (the reference API has no slab form of this call)"),
             "_lib": lib, "_shape": shape, "_variant": variant}
 
 

@@ -36,6 +36,9 @@ def load_ref(variant):
     lib.fn2refTimedGridMT.argtypes = [P, P, I, I, I, I, F, F, F, F, I, I, P]
     lib.fn2refTimedPositionsMT.restype = ctypes.c_double
     lib.fn2refTimedPositionsMT.argtypes = [P, P, I, I, P, P, P, P, I, I, P]
+    if hasattr(lib, "fn2refTimedTileableMT"):  # oracle builds older than the threaded tileable driver lack it
+        lib.fn2refTimedTileableMT.restype = ctypes.c_double
+        lib.fn2refTimedTileableMT.argtypes = [P, P, I, I, F, F, I, I, P]
     if hasattr(lib, "fn2refCanonicalEncodedNodeTree"):       # the reference's own DeserialiseNodeData + SerialiseNodeData (oracle/ref/ref_extra.cpp)
         lib.fn2refCanonicalEncodedNodeTree.restype = ctypes.c_long
         lib.fn2refCanonicalEncodedNodeTree.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_long]

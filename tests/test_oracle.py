@@ -138,3 +138,23 @@ def test_port_oracle_out_of_range_enums_vs_strict_ref(ref, port):
         assert a.supported, name
         assert same(a.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 31)[0], b.grid3d(-3.3, 2.1, 0.7, 10, 10, 10, 1.9, 1.7, 2.3, 31)[0]), name
         assert same(a.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, 31)[0], b.grid4d(-3.3, 2.1, 0.7, -1.9, 6, 6, 6, 6, 1.9, 1.7, 2.3, 1.1, 31)[0]), name
+
+
+def test_threaded_tileable_timing_driver_tracks_the_reference_call(ref, fn):
+    """bench.py's CPU baseline for the tileable config splits the rows across threads through the reference's GenPositionArray4D
+    (GenTileable2D has no slab form). It is a timing driver -- its positions come from libm, not FS::Cos / FS::Sin -- so it must
+    follow fnGenTileable2D closely, not bit for bit, and must not depend on the thread count."""
+    if not hasattr(ref, "fn2refTimedTileableMT"):
+        pytest.skip("oracle/_ref built before the threaded tileable driver existed")
+    node = helpers.RefNode(ref, fn.TREES["c2_fbm5_perlin"])
+    nx, ny = 96, 40
+    want = np.empty(nx * ny, np.float32)
+    ref.fnGenTileable2D(node.handle, want.ctypes.data, nx, ny, 1.0, 0.5, 1337, None)
+    outs = []
+    for threads in (1, 3, 7):
+        got = np.empty(nx * ny, np.float32)
+        mm = np.zeros(2, np.float32)
+        assert ref.fn2refTimedTileableMT(node.handle, got.ctypes.data, nx, ny, 1.0, 0.5, 1337, threads, mm.ctypes.data) > 0
+        assert np.abs(got - want).max() < 2e-2 and mm[0] == got.min() and mm[1] == got.max()
+        outs.append(got)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
