@@ -798,7 +798,7 @@ namespace FastNoise
             // reduction) is paid once per that many groups, while the grid stays many waves deep -- the hardware block scheduler
             // keeps balancing the SMs to the end of the call. (A grid of exactly the resident blocks, every thread walking the whole
             // call, measured 11 % SLOWER on the heavy trees: warps that the issue arbiter favours finish early and the tail runs
-            // under-occupied. profiles/r2_perf_sweep.txt) Never fewer blocks than the device keeps resident.
+            // under-occupied. profiles/r2_perf_sweep_b_launch_geometry.txt) Never fewer blocks than the device keeps resident.
             // Above kConvergedCodeBytes of loop body one group per thread: the warps of a block then run through the code together,
             // one instruction stream per block. Walking several groups they drift apart, every warp fetches its own stream, and the
             // instruction cache thrashes (terrain tree, 55 KB: ICC hit rate 70 %, "no instruction" the top stall, -11 %).
