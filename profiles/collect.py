@@ -47,6 +47,7 @@ def main():
                      ("odd_width", "r2_odd_width.txt"), ("node_benchmark", "r2_node_benchmark_b200.txt"),
                      ("node_benchmark_trees", "r2_node_benchmark_trees_b200.txt"), ("smoke", "r2_smoke.txt"), ("d2h_bandwidth", "r2_d2h_bandwidth_1gpu.txt")):
         shutil.copyfile("%s/%s_%s.txt" % (OUT, src, tag), os.path.join(HERE, dst))
+    shutil.copyfile(os.path.join(OUT, "fullsize_parity.txt"), os.path.join(HERE, "r2_fullsize_parity.txt"))  # written by tests/test_gpu_fullsize.py
     # (r2_pageable_probe.txt keeps the thread-count x streaming-store sweep; the final library's own line goes beside it)
     shutil.copyfile("%s/pageable_probe_%s.txt" % (OUT, tag), os.path.join(HERE, "r2_pageable_probe_final.txt"))
     print(open(os.path.join(HERE, "r2_ncu_summary.md")).read())
