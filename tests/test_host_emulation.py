@@ -348,3 +348,55 @@ def test_any_width_four_point_groups_on_host(fn, ref, tmp_path, monkeypatch):
         if not same(out, want):
             failures.append((dims, n, helpers.compare(out, want)))
     assert not failures, failures
+
+
+def _weighted_fractal(fn, ref_lib, node_id):
+    """FractalFBm (13) / FractalRidged (15) / DomainWarpFractal (19, 20) at their default octave counts with a weighted strength of 0.5."""
+    tree = _Handles(fn, ref_lib, node_id)
+    if node_id in (19, 20):
+        warp = _Handles(fn, ref_lib, 18)
+        warp.both("fnSetNodeLookup", 0, warp.leaf(6, 41.0))
+        tree.ours += warp.ours
+        tree.theirs += warp.theirs
+        tree.both("fnSetNodeLookup", 0, (warp.ours[0].handle, warp.theirs[0]))
+    else:
+        tree.both("fnSetNodeLookup", 0, tree.leaf(6, 37.0))
+    tree.both("fnSetHybridFloat", 1, ctypes.c_float(0.5))  # hybrid 0 = Gain, 1 = Weighted Strength
+    return tree
+
+
+def test_code_shape_knobs_are_bit_neutral_on_host(fn, ref, tmp_path, monkeypatch):
+    """The A/B knobs of the lowering (profiles/perf_sweep*.sh) only change the SHAPE of the generated code: the divergent group walk
+    (FASTNOISE2_B200_CONVERGENT=0, the round-1 form) and one-body octave loops (FASTNOISE2_B200_ONE_BODY=1 / 2: the first octave runs
+    inside the loop, sum starts at -0.0f) must give the oracle's bits -- config trees, and fractals / domain-warp fractals with a
+    weighted strength (their per-octave amplitude update moves to the end of the loop body)."""
+    failures = []
+    n, off, step = (12, 7, 5), (0.5, -2.0, 3.0), (1.3, 1.1, 0.9)
+
+    def check(label, holder, text, reference):
+        lib, (ppt, params) = build_on_host(holder, text, 3, str(tmp_path), "shape")
+        out = np.zeros(int(np.prod(n)), np.float32)
+        lib.fn2_host_grid(out.ctypes.data_as(ctypes.c_void_p), 3, (ctypes.c_float * 3)(*off), (ctypes.c_int * 3)(*n),
+                          (ctypes.c_float * 3)(*step), 7, ppt, params.ctypes.data_as(ctypes.c_void_p), len(params))
+        want = reference()
+        if not same(out, want):
+            failures.append((label, helpers.compare(out, want)))
+
+    for one_body, convergent in (("1", "1"), ("1", "0"), ("0", "0"), ("2", "1")):
+        monkeypatch.setenv("FASTNOISE2_B200_ONE_BODY", one_body)
+        monkeypatch.setenv("FASTNOISE2_B200_CONVERGENT", convergent)
+        for name in ("c4_terrain", "c2_fbm5_perlin"):
+            node = helpers.RefNode(ref, fn.TREES[name])
+            check((one_body, convergent, name), fn, fn.TREES[name], lambda: node.grid3d(*off, *n, *step, 7)[0])
+        for node_id in (13, 15, 19, 20):
+            tree = _weighted_fractal(fn, ref, node_id)
+            holder = type("OneTree", (), {"Generator": staticmethod(lambda text, g=tree.ours[0]: g)})
+
+            def reference():
+                want, mm = np.empty(int(np.prod(n)), np.float32), np.zeros(2, np.float32)
+                ref.fnGenUniformGrid3D(tree.theirs[0], want.ctypes.data, *off, *n, *step, 7, mm.ctypes.data)
+                return want
+            assert "weightedStrength" in tree.ours[0].kernel_source(3)
+            check((one_body, convergent, node_id), holder, "", reference)
+            tree.close()
+    assert not failures, failures
