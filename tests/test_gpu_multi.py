@@ -134,6 +134,31 @@ def _rank_main(rank, world, port, tmp):
     assert torch.equal(got, whole), "shared volume differs on rank %d" % rank
     assert (float(mm3[0]), float(mm3[1])) == mm_whole
     assert lib.fnb200CommFreeVolume(comm, shared, sp) == 0
+    # the same fused path on rows 4 does not divide (the any-width four-point entry: groups straddle rows, so a group's peer
+    # stores may be scalar at the slab's end) -- forced onto the large-call path, the volume is small
+    os.environ["FASTNOISE2_B200_FILL"] = "0"
+    os.environ["FASTNOISE2_B200_RAGGED"] = "2"
+    m = (130, 7, 2 * world + 1)
+    per2 = m[0] * m[1]
+    b2, e2 = slab_range(m[2], rank, world)
+    shared2 = lib.fnb200CommAllocVolume(comm, per2 * m[2], sp)
+    assert shared2, fn.last_error()
+    with torch.cuda.stream(stream):
+        assert lib.fnb200MinMaxReset(acc.data_ptr(), sp) == 0
+        assert lib.fnb200GenUniformGrid3DShared(g.handle, shared2, 0.0, 0.0, 0.0, m[0], m[1], m[2], 2.7, 2.7, 2.7, 1337, b2, e2, acc.data_ptr(), sp) == 0, fn.last_error()
+        assert lib.fnb200CommAllReduceMinMax(comm, acc.data_ptr(), sp) == 0
+        mm4 = np.zeros(2, np.float32)
+        assert lib.fnb200MinMaxRead(acc.data_ptr(), sp, mm4.ctypes.data) == 0
+        got2 = torch.empty(per2 * m[2], dtype=torch.float32, device="cuda")
+        ct.cdll.LoadLibrary("libcudart.so.12").cudaMemcpyAsync(ct.c_void_p(got2.data_ptr()), ct.c_void_p(lib.fnb200VolumeData(shared2)), ct.c_size_t(per2 * m[2] * 4), 3, ct.c_void_p(sp))
+    stream.synchronize()
+    whole2 = torch.empty(per2 * m[2], dtype=torch.float32, device="cuda")
+    mm_whole2 = g.grid3d(whole2, 0.0, 0.0, 0.0, *m, 2.7, 2.7, 2.7, 1337)
+    assert torch.equal(got2, whole2), "any-width shared volume differs on rank %d" % rank
+    assert (float(mm4[0]), float(mm4[1])) == mm_whole2
+    assert lib.fnb200CommFreeVolume(comm, shared2, sp) == 0
+    os.environ.pop("FASTNOISE2_B200_FILL", None)
+    os.environ.pop("FASTNOISE2_B200_RAGGED", None)
     assert lib.fnb200CommDestroy(comm) == 0
     dist.destroy_process_group()
     open(os.path.join(tmp, "rank%d.ok" % rank), "w").write("ok")
