@@ -695,7 +695,9 @@ namespace FastNoise
                 if( lowered.source != v.source || v.mathMode != mode )
                 {
                     v.source = std::move( lowered.source );
-                    v.sourceHash = Fnv64( v.source, Fnv64( "math mode " + std::to_string( mode ) ) );
+                    // (extra NVRTC flags are part of the key: the loaded-kernel table must not hand back a kernel built with others)
+                    const char* extraFlags = std::getenv( "FASTNOISE2_B200_NVRTC_FLAGS" );
+                    v.sourceHash = Fnv64( v.source, Fnv64( "math mode " + std::to_string( mode ) + " flags " + ( extraFlags ? extraFlags : "" ) + " block " + std::to_string( BlockThreads() ) ) );
                 }
                 v.params = std::move( lowered.params );
                 v.error = std::move( lowered.error );
