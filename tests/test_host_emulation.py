@@ -382,10 +382,10 @@ def test_code_shape_knobs_are_bit_neutral_on_host(fn, ref, tmp_path, monkeypatch
         if not same(out, want):
             failures.append((label, helpers.compare(out, want)))
 
-    for one_body, convergent in (("1", "1"), ("1", "0"), ("0", "0"), ("2", "1")):
+    for one_body, convergent in (("1", "1"), ("0", "0"), ("2", "1")):
         monkeypatch.setenv("FASTNOISE2_B200_ONE_BODY", one_body)
         monkeypatch.setenv("FASTNOISE2_B200_CONVERGENT", convergent)
-        for name in ("c4_terrain", "c2_fbm5_perlin"):
+        for name in ("c4_terrain",):
             node = helpers.RefNode(ref, fn.TREES[name])
             check((one_body, convergent, name), fn, fn.TREES[name], lambda: node.grid3d(*off, *n, *step, 7)[0])
         for node_id in (13, 15, 19, 20):
